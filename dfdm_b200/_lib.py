@@ -1,0 +1,119 @@
+"""
+ctypes binding of the C ABI declared in ``include/dfdm_b200.h``.
+
+This is the stub a maintainer of the reference would add to call the CUDA path from
+``EquilibriumModel.__call__`` / ``Loss.__call__`` / ``Optimizer.minimize``.
+The library is built in-tree by ``python -m dfdm_b200.build``; there is no fallback implementation:
+if the shared object cannot be loaded, importing this module raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdfdm_b200.so")
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
+STATUS_OK, STATUS_SINGULAR, STATUS_NOT_CONVERGED, STATUS_NONFINITE = 0, 1, 2, 3
+SOLVER_AUTO, SOLVER_DIRECT, SOLVER_PCG = 0, 1, 2
+SOLVERS = {"auto": SOLVER_AUTO, "direct": SOLVER_DIRECT, "pcg": SOLVER_PCG}
+
+ARR_FREE, ARR_FIXED, ARR_FREEFIXED, ARR_ROWPTR, ARR_COLIDX, ARR_EDGE_SLOTS, ARR_SOLVER_PERM = range(7)
+ARR_NODE_INC_PTR, ARR_NODE_INC_EDGE, ARR_NODE_INC_SIGN = 7, 8, 9
+
+GOAL_KINDS = {"NodePoint": 0, "NodeLine": 1, "NodePlane": 2, "NodeResidualForce": 3, "NodeResidualVector": 4,
+              "NodeResidualDirection": 5, "EdgeLength": 6, "EdgeForce": 7, "EdgeLoadPath": 8, "EdgeVectorAngle": 9,
+              "EdgeDirection": 10, "NetworkLoadPath": 11}
+GOAL_NPARAMS = 6
+TERM_KINDS = {"SquaredError": 0, "MeanSquaredError": 1, "PredictionError": 2}
+
+# every symbol include/dfdm_b200.h declares
+SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan_destroy", "dfdm_plan_get_info",
+           "dfdm_plan_array", "dfdm_goalprog_create", "dfdm_goalprog_destroy", "dfdm_workspace_bytes", "dfdm_forward",
+           "dfdm_loss_and_grad", "dfdm_vjp", "dfdm_forward_host", "dfdm_loss_and_grad_host", "dfdm_launch_count",
+           "dfdm_last_pcg_iterations"]
+
+
+class Options(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("pcg_maxiter", C.c_int32), ("pcg_rtol", C.c_double),
+                ("pcg_check_every", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32), ("n_fixed", C.c_int32),
+                ("nnz", C.c_int32), ("bandwidth_natural", C.c_int32), ("bandwidth_solver", C.c_int32),
+                ("direct_fits", C.c_int32), ("direct_smem_bytes", C.c_int64), ("auto_solver", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class DfdmError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("dfdm_b200: %s is missing; build it with `python -m dfdm_b200.build` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.dfdm_last_error.restype = C.c_char_p
+    lib.dfdm_abi_version.restype = i32
+    lib.dfdm_plan_create.argtypes = [i32, i32, vp, vp, C.POINTER(vp)]
+    lib.dfdm_plan_destroy.argtypes = [vp]
+    lib.dfdm_plan_destroy.restype = None
+    lib.dfdm_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
+    lib.dfdm_plan_array.argtypes = [vp, i32, C.POINTER(i64)]
+    lib.dfdm_plan_array.restype = C.POINTER(i32)
+    lib.dfdm_goalprog_create.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, dbl, C.POINTER(vp)]
+    lib.dfdm_goalprog_destroy.argtypes = [vp]
+    lib.dfdm_goalprog_destroy.restype = None
+    lib.dfdm_workspace_bytes.argtypes = [vp, i32, C.POINTER(Options)]
+    lib.dfdm_workspace_bytes.restype = i64
+    lib.dfdm_forward.argtypes = [vp, i32] + [vp] * 3 + [vp] * 5 + [vp, vp, i64, C.POINTER(Options), vp]
+    lib.dfdm_loss_and_grad.argtypes = [vp, vp, i32] + [vp] * 3 + [vp, vp] + [vp] * 5 + [vp, vp, i64, C.POINTER(Options), vp]
+    lib.dfdm_vjp.argtypes = [vp, i32] + [vp] * 3 + [vp] * 5 + [vp, vp, vp, i64, C.POINTER(Options), vp]
+    lib.dfdm_forward_host.argtypes = [vp, i32] + [vp] * 3 + [vp] * 5 + [vp, C.POINTER(Options)]
+    lib.dfdm_loss_and_grad_host.argtypes = [vp, vp, i32] + [vp] * 3 + [vp, vp, vp, C.POINTER(Options)]
+    lib.dfdm_launch_count.restype = i64
+    lib.dfdm_last_pcg_iterations.argtypes = [C.POINTER(i32), C.POINTER(i32)]
+    lib.dfdm_last_pcg_iterations.restype = None
+    for name in SYMBOLS:
+        getattr(lib, name)
+    if lib.dfdm_abi_version() != 1:
+        raise ImportError("dfdm_b200: ABI version mismatch between _lib.py and libdfdm_b200.so")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != OK:
+        raise DfdmError("dfdm_b200 error %d: %s" % (rc, (lib.dfdm_last_error() or b"").decode()))
+
+
+def make_options(solver="auto", pcg_maxiter=0, pcg_rtol=0.0, pcg_check_every=0):
+    if isinstance(solver, str):
+        solver = SOLVERS[solver]
+    return Options(solver, int(pcg_maxiter), float(pcg_rtol), int(pcg_check_every), 0)
+
+
+def plan_array(handle, which):
+    length = C.c_int64(0)
+    ptr = lib.dfdm_plan_array(handle, which, C.byref(length))
+    if not ptr:
+        raise DfdmError((lib.dfdm_last_error() or b"").decode())
+    if length.value == 0:
+        return np.zeros(0, dtype=np.int32)
+    return np.ctypeslib.as_array(ptr, shape=(length.value,)).copy()
+
+
+def launch_count():
+    return int(lib.dfdm_launch_count())
+
+
+def last_pcg_iterations():
+    f, a = C.c_int32(0), C.c_int32(0)
+    lib.dfdm_last_pcg_iterations(C.byref(f), C.byref(a))
+    return f.value, a.value

@@ -1,0 +1,405 @@
+// C ABI (include/dfdm_b200.h): plan / goal-program lifetime, device mirrors, dispatch.
+#include <cstring>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dfdm {
+
+std::atomic<long long> g_launches{0};
+void last_pcg_iterations(int* fwd, int* adj);
+
+// ---- device mirrors ------------------------------------------------------------------------------
+
+static int upload_plan(const Plan& P, int device, PlanDev& out) {
+    std::lock_guard<std::mutex> lock(P.mu);
+    auto it = P.dev.find(device);
+    if (it != P.dev.end()) {
+        out = it->second;
+        return DFDM_OK;
+    }
+    const std::vector<int32_t>* arrays[] = {&P.edges, &P.node_src, &P.free_nodes, &P.rowptr, &P.colidx, &P.diagslot,
+                                            &P.finc_ptr, &P.finc_edge, &P.finc_code, &P.ninc_ptr, &P.ninc_edge, &P.ninc_sign,
+                                            &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code};
+    constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
+    int64_t offs[NA], total = 0;
+    for (int k = 0; k < NA; ++k) {
+        offs[k] = total;
+        total += ((int64_t)arrays[k]->size() * 4 + 255) & ~(int64_t)255;
+    }
+    char* block = nullptr;
+    DFDM_CUDA_OK(cudaMalloc(&block, (size_t)std::max<int64_t>(total, 256)));
+    for (int k = 0; k < NA; ++k)
+        if (!arrays[k]->empty())
+            DFDM_CUDA_OK(cudaMemcpy(block + offs[k], arrays[k]->data(), arrays[k]->size() * 4, cudaMemcpyHostToDevice));
+    auto at = [&](int k) { return reinterpret_cast<const int32_t*>(block + offs[k]); };
+    PlanDev d;
+    d.n = P.n; d.E = P.E; d.nf = P.nf; d.nx = P.nx; d.nnz = P.nnz; d.w = P.w;
+    d.edges = at(0); d.node_src = at(1); d.free_nodes = at(2); d.rowptr = at(3); d.colidx = at(4); d.diagslot = at(5);
+    d.finc_ptr = at(6); d.finc_edge = at(7); d.finc_code = at(8); d.ninc_ptr = at(9); d.ninc_edge = at(10); d.ninc_sign = at(11);
+    d.perm = at(12); d.pos = at(13); d.sinc_ptr = at(14); d.sinc_edge = at(15); d.sinc_code = at(16);
+    P.dev[device] = d;
+    P.dev_block[device] = block;
+    out = d;
+    return DFDM_OK;
+}
+
+static int upload_prog(const GoalProg& G, int device, GoalProgDev& out) {
+    std::lock_guard<std::mutex> lock(G.mu);
+    auto it = G.dev.find(device);
+    if (it != G.dev.end()) {
+        out = it->second;
+        return DFDM_OK;
+    }
+    int64_t rec_bytes = ((int64_t)G.recs.size() * sizeof(GoalRec) + 255) & ~(int64_t)255;
+    int64_t np_bytes = ((int64_t)G.ngoal_ptr.size() * 4 + 255) & ~(int64_t)255;
+    int64_t ep_bytes = ((int64_t)G.egoal_ptr.size() * 4 + 255) & ~(int64_t)255;
+    char* block = nullptr;
+    DFDM_CUDA_OK(cudaMalloc(&block, (size_t)(rec_bytes + np_bytes + ep_bytes + 256)));
+    if (!G.recs.empty()) DFDM_CUDA_OK(cudaMemcpy(block, G.recs.data(), G.recs.size() * sizeof(GoalRec), cudaMemcpyHostToDevice));
+    DFDM_CUDA_OK(cudaMemcpy(block + rec_bytes, G.ngoal_ptr.data(), G.ngoal_ptr.size() * 4, cudaMemcpyHostToDevice));
+    DFDM_CUDA_OK(cudaMemcpy(block + rec_bytes + np_bytes, G.egoal_ptr.data(), G.egoal_ptr.size() * 4, cudaMemcpyHostToDevice));
+    GoalProgDev d;
+    d.n_goals = (int)G.recs.size();
+    d.n_net = G.n_net;
+    d.net_begin = G.net_begin;
+    d.recs = reinterpret_cast<const GoalRec*>(block);
+    d.ngoal_ptr = reinterpret_cast<const int32_t*>(block + rec_bytes);
+    d.egoal_ptr = reinterpret_cast<const int32_t*>(block + rec_bytes + np_bytes);
+    d.l2_alpha = G.l2_alpha;
+    G.dev[device] = d;
+    G.dev_block[device] = block;
+    out = d;
+    return DFDM_OK;
+}
+
+static int resolve_solver(const Plan& P, const dfdm_options* opt, int& solver) {
+    bool fits = direct_smem_bytes(P.nf, P.w) <= kDirectSmemLimit;
+    solver = opt ? opt->solver : DFDM_SOLVER_AUTO;
+    if (solver == DFDM_SOLVER_AUTO) solver = fits ? DFDM_SOLVER_DIRECT : DFDM_SOLVER_PCG;
+    if (solver == DFDM_SOLVER_DIRECT && !fits) {
+        set_error("direct solver requested but the banded factor (" + std::to_string(direct_smem_bytes(P.nf, P.w)) +
+                  " bytes) does not fit one CTA's shared memory; use DFDM_SOLVER_PCG");
+        return DFDM_EUNSUPPORTED;
+    }
+    if (solver != DFDM_SOLVER_DIRECT && solver != DFDM_SOLVER_PCG) {
+        set_error("unknown solver id");
+        return DFDM_EINVAL;
+    }
+    return DFDM_OK;
+}
+
+static int dispatch(const dfdm_plan* plan, const dfdm_goalprog* prog, Eval& ev, const dfdm_options* opt) {
+    if (!plan || ev.B <= 0 || !ev.q || !ev.loads || (plan->nx > 0 && !ev.xfix)) {
+        set_error("NULL plan / inputs or non-positive batch");
+        return DFDM_EINVAL;
+    }
+    if (prog && (prog->n != plan->n || prog->E != plan->E)) {
+        set_error("goal program was compiled for a different plan");
+        return DFDM_EINVAL;
+    }
+    if (ev.adjoint && !ev.dq) {
+        set_error("gradient requested without an output buffer");
+        return DFDM_EINVAL;
+    }
+    int device = 0;
+    DFDM_CUDA_OK(cudaGetDevice(&device));
+    int rc = upload_plan(*plan, device, ev.P);
+    if (rc) return rc;
+    ev.has_prog = prog != nullptr;
+    if (prog) {
+        rc = upload_prog(*prog, device, ev.G);
+        if (rc) return rc;
+    }
+    if (opt) ev.opt = *opt;
+    int solver = 0;
+    rc = resolve_solver(*plan, opt, solver);
+    if (rc) return rc;
+    return solver == DFDM_SOLVER_DIRECT ? run_direct(ev) : run_pcg(ev);
+}
+
+// cached device arena for the *_host entry points
+static int arena_get(const Plan& P, int device, int64_t bytes, char** out) {
+    std::lock_guard<std::mutex> lock(P.mu);
+    Plan::Arena& a = P.arena[device];
+    if (a.bytes < bytes) {
+        if (a.ptr) cudaFree(a.ptr);
+        a.ptr = nullptr;
+        a.bytes = 0;
+        DFDM_CUDA_OK(cudaMalloc(&a.ptr, (size_t)bytes));
+        a.bytes = bytes;
+    }
+    *out = static_cast<char*>(a.ptr);
+    return DFDM_OK;
+}
+
+}  // namespace dfdm
+
+using namespace dfdm;
+
+extern "C" {
+
+int dfdm_plan_create(int32_t n, int32_t n_edges, const int32_t* edges, const uint8_t* is_fixed, dfdm_plan** plan) {
+    if (!plan) {
+        set_error("dfdm_plan_create: NULL output pointer");
+        return DFDM_EINVAL;
+    }
+    *plan = nullptr;
+    dfdm_plan* p = new dfdm_plan();
+    int rc = build_plan(n, n_edges, edges, is_fixed, *p);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    *plan = p;
+    return DFDM_OK;
+}
+
+void dfdm_plan_destroy(dfdm_plan* plan) {
+    if (!plan) return;
+    for (auto& kv : plan->dev_block) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second);
+        cudaSetDevice(prev);
+    }
+    for (auto& kv : plan->arena) {
+        if (!kv.second.ptr) continue;
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.ptr);
+        cudaSetDevice(prev);
+    }
+    delete plan;
+}
+
+int dfdm_goalprog_create(const dfdm_plan* plan, int32_t n_goals, const int32_t* kind, const int32_t* element,
+                         const int32_t* term, const double* weight, const double* params, int32_t n_terms,
+                         const int32_t* term_kind, const double* term_alpha, double l2_alpha, dfdm_goalprog** prog) {
+    if (!plan || !prog || n_goals < 0 || n_terms < 0 || (n_goals > 0 && (!kind || !element || !term || !weight || !params)) ||
+        (n_terms > 0 && (!term_kind || !term_alpha))) {
+        set_error("dfdm_goalprog_create: NULL or negative argument");
+        return DFDM_EINVAL;
+    }
+    *prog = nullptr;
+    // entries per term (vector goals count 3) for the mean of MeanSquaredError (losses.py:55)
+    std::vector<int64_t> entries(n_terms, 0);
+    for (int g = 0; g < n_goals; ++g) {
+        if (kind[g] < 0 || kind[g] >= DFDM_N_GOAL_KINDS || term[g] < 0 || term[g] >= n_terms) {
+            set_error("dfdm_goalprog_create: goal " + std::to_string(g) + " has an unknown kind or term");
+            return DFDM_EINVAL;
+        }
+        bool node = kind[g] <= DFDM_GOAL_NODE_RESIDUAL_DIRECTION, net = kind[g] == DFDM_GOAL_NETWORK_LOAD_PATH;
+        if (!net && (element[g] < 0 || element[g] >= (node ? plan->n : plan->E))) {
+            set_error("dfdm_goalprog_create: goal " + std::to_string(g) + " references an element out of range");
+            return DFDM_EINVAL;
+        }
+        bool vec = kind[g] == DFDM_GOAL_NODE_POINT || kind[g] == DFDM_GOAL_NODE_LINE || kind[g] == DFDM_GOAL_NODE_PLANE ||
+                   kind[g] == DFDM_GOAL_NODE_RESIDUAL_VECTOR || kind[g] == DFDM_GOAL_NODE_RESIDUAL_DIRECTION ||
+                   kind[g] == DFDM_GOAL_EDGE_DIRECTION;
+        entries[term[g]] += vec ? 3 : 1;
+    }
+    for (int t = 0; t < n_terms; ++t)
+        if (term_kind[t] < DFDM_TERM_SQUARED_ERROR || term_kind[t] > DFDM_TERM_PREDICTION_ERROR) {
+            set_error("dfdm_goalprog_create: unknown term kind");
+            return DFDM_EINVAL;
+        }
+    dfdm_goalprog* G = new dfdm_goalprog();
+    G->n = plan->n;
+    G->E = plan->E;
+    G->l2_alpha = l2_alpha;
+    // stable bucket sort: node goals by node, edge goals by edge, then network goals
+    std::vector<int32_t> order(n_goals);
+    for (int g = 0; g < n_goals; ++g) order[g] = g;
+    auto key = [&](int g) -> int64_t {
+        if (kind[g] <= DFDM_GOAL_NODE_RESIDUAL_DIRECTION) return element[g];
+        if (kind[g] == DFDM_GOAL_NETWORK_LOAD_PATH) return (int64_t)plan->n + plan->E;
+        return (int64_t)plan->n + element[g];
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+    G->ngoal_ptr.assign(plan->n + 1, 0);
+    G->egoal_ptr.assign(plan->E + 1, 0);
+    G->recs.resize(n_goals);
+    int n_node = 0, n_edge = 0;
+    for (int s = 0; s < n_goals; ++s) {
+        int g = order[s];
+        GoalRec& r = G->recs[s];
+        r.kind = kind[g];
+        r.elem = element[g];
+        int tk = term_kind[term[g]];
+        r.mode = tk == DFDM_TERM_PREDICTION_ERROR ? 1 : 0;
+        r.pad = 0;
+        r.scale = term_alpha[term[g]];
+        if (tk == DFDM_TERM_MEAN_SQUARED_ERROR) r.scale /= (double)entries[term[g]];
+        r.weight = weight[g];
+        for (int k = 0; k < DFDM_GOAL_NPARAMS; ++k) r.p[k] = params[(size_t)g * DFDM_GOAL_NPARAMS + k];
+        if (kind[g] <= DFDM_GOAL_NODE_RESIDUAL_DIRECTION) {
+            G->ngoal_ptr[element[g] + 1]++;
+            n_node++;
+        } else if (kind[g] != DFDM_GOAL_NETWORK_LOAD_PATH) {
+            G->egoal_ptr[element[g] + 1]++;
+            n_edge++;
+        }
+    }
+    for (int i = 0; i < plan->n; ++i) G->ngoal_ptr[i + 1] += G->ngoal_ptr[i];
+    G->egoal_ptr[0] = n_node;
+    for (int e = 0; e < plan->E; ++e) G->egoal_ptr[e + 1] += G->egoal_ptr[e];
+    G->net_begin = n_node + n_edge;
+    G->n_net = n_goals - G->net_begin;
+    *prog = G;
+    return DFDM_OK;
+}
+
+void dfdm_goalprog_destroy(dfdm_goalprog* prog) {
+    if (!prog) return;
+    for (auto& kv : prog->dev_block) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second);
+        cudaSetDevice(prev);
+    }
+    delete prog;
+}
+
+int64_t dfdm_workspace_bytes(const dfdm_plan* plan, int32_t batch, const dfdm_options* options) {
+    if (!plan || batch <= 0) {
+        set_error("dfdm_workspace_bytes: NULL plan or non-positive batch");
+        return DFDM_EINVAL;
+    }
+    int solver = 0;
+    int rc = resolve_solver(*plan, options, solver);
+    if (rc) return rc;
+    return solver == DFDM_SOLVER_DIRECT ? direct_workspace(*plan, batch, true, true) : pcg_workspace(*plan, batch);
+}
+
+int dfdm_forward(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
+                 double* xyz, double* residuals, double* vectors, double* lengths, double* forces, int32_t* status,
+                 void* workspace, int64_t workspace_bytes, const dfdm_options* options, void* stream) {
+    Eval ev;
+    ev.B = batch; ev.q = q; ev.loads = loads; ev.xfix = xyz_fixed;
+    ev.o_xyz = xyz; ev.o_res = residuals; ev.o_vec = vectors; ev.o_len = lengths; ev.o_for = forces;
+    ev.status = status; ev.ws = static_cast<char*>(workspace); ev.ws_bytes = workspace_bytes;
+    ev.stream = static_cast<cudaStream_t>(stream);
+    return dispatch(plan, nullptr, ev, options);
+}
+
+int dfdm_loss_and_grad(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t batch, const double* q, const double* loads,
+                       const double* xyz_fixed, double* loss, double* dq, double* xyz, double* residuals, double* vectors,
+                       double* lengths, double* forces, int32_t* status, void* workspace, int64_t workspace_bytes,
+                       const dfdm_options* options, void* stream) {
+    if (!prog || !loss) {
+        set_error("dfdm_loss_and_grad: NULL goal program or loss buffer");
+        return DFDM_EINVAL;
+    }
+    Eval ev;
+    ev.B = batch; ev.q = q; ev.loads = loads; ev.xfix = xyz_fixed;
+    ev.o_xyz = xyz; ev.o_res = residuals; ev.o_vec = vectors; ev.o_len = lengths; ev.o_for = forces;
+    ev.loss = loss; ev.dq = dq; ev.adjoint = dq != nullptr;
+    ev.status = status; ev.ws = static_cast<char*>(workspace); ev.ws_bytes = workspace_bytes;
+    ev.stream = static_cast<cudaStream_t>(stream);
+    return dispatch(plan, prog, ev, options);
+}
+
+int dfdm_vjp(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
+             const double* xyz_bar, const double* residuals_bar, const double* vectors_bar, const double* lengths_bar,
+             const double* forces_bar, double* dq, int32_t* status, void* workspace, int64_t workspace_bytes,
+             const dfdm_options* options, void* stream) {
+    Eval ev;
+    ev.B = batch; ev.q = q; ev.loads = loads; ev.xfix = xyz_fixed;
+    ev.c_xyz = xyz_bar; ev.c_res = residuals_bar; ev.c_vec = vectors_bar; ev.c_len = lengths_bar; ev.c_for = forces_bar;
+    ev.dq = dq; ev.adjoint = true;
+    ev.status = status; ev.ws = static_cast<char*>(workspace); ev.ws_bytes = workspace_bytes;
+    ev.stream = static_cast<cudaStream_t>(stream);
+    return dispatch(plan, nullptr, ev, options);
+}
+
+// ---- host-buffer variants -------------------------------------------------------------------------
+
+static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B, const double* q, const double* loads,
+                     const double* xyz_fixed, double* loss, double* dq, double* xyz, double* residuals, double* vectors,
+                     double* lengths, double* forces, int32_t* status, const dfdm_options* options) {
+    if (!plan || B <= 0 || !q || !loads) {
+        set_error("host evaluation: NULL plan / inputs or non-positive batch");
+        return DFDM_EINVAL;
+    }
+    int device = 0;
+    DFDM_CUDA_OK(cudaGetDevice(&device));
+    const int64_t n = plan->n, E = plan->E, nx = plan->nx;
+    int64_t ws_bytes = dfdm_workspace_bytes(plan, B, options);
+    if (ws_bytes < 0) return (int)ws_bytes;
+    Bump io(nullptr);
+    auto layout = [&](Bump& bump, double*& d_q, double*& d_loads, double*& d_xfix, double*& d_loss, double*& d_dq, double*& d_xyz,
+                      double*& d_res, double*& d_vec, double*& d_len, double*& d_for, int32_t*& d_status, char*& d_ws) {
+        d_q = bump.take<double>(B * E);
+        d_loads = bump.take<double>(n * 3);
+        d_xfix = bump.take<double>(std::max<int64_t>(nx * 3, 1));
+        d_loss = loss ? bump.take<double>(B) : nullptr;
+        d_dq = dq ? bump.take<double>(B * E) : nullptr;
+        d_xyz = xyz ? bump.take<double>(B * n * 3) : nullptr;
+        d_res = residuals ? bump.take<double>(B * n * 3) : nullptr;
+        d_vec = vectors ? bump.take<double>(B * E * 3) : nullptr;
+        d_len = lengths ? bump.take<double>(B * E) : nullptr;
+        d_for = forces ? bump.take<double>(B * E) : nullptr;
+        d_status = bump.take<int32_t>(B);
+        d_ws = bump.take<char>(ws_bytes);
+    };
+    double *d_q, *d_loads, *d_xfix, *d_loss, *d_dq, *d_xyz, *d_res, *d_vec, *d_len, *d_for;
+    int32_t* d_status;
+    char* d_ws;
+    layout(io, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws);
+    char* base = nullptr;
+    int rc = arena_get(*plan, device, io.off, &base);
+    if (rc) return rc;
+    Bump real(base);
+    layout(real, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws);
+    cudaStream_t st = nullptr;
+    DFDM_CUDA_OK(cudaMemcpyAsync(d_q, q, sizeof(double) * B * E, cudaMemcpyHostToDevice, st));
+    DFDM_CUDA_OK(cudaMemcpyAsync(d_loads, loads, sizeof(double) * n * 3, cudaMemcpyHostToDevice, st));
+    if (nx > 0) DFDM_CUDA_OK(cudaMemcpyAsync(d_xfix, xyz_fixed, sizeof(double) * nx * 3, cudaMemcpyHostToDevice, st));
+    if (prog)
+        rc = dfdm_loss_and_grad(plan, prog, B, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws,
+                                ws_bytes, options, st);
+    else
+        rc = dfdm_forward(plan, B, d_q, d_loads, d_xfix, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws, ws_bytes, options, st);
+    if (rc) return rc;
+    if (loss) DFDM_CUDA_OK(cudaMemcpyAsync(loss, d_loss, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (dq) DFDM_CUDA_OK(cudaMemcpyAsync(dq, d_dq, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
+    if (xyz) DFDM_CUDA_OK(cudaMemcpyAsync(xyz, d_xyz, sizeof(double) * B * n * 3, cudaMemcpyDeviceToHost, st));
+    if (residuals) DFDM_CUDA_OK(cudaMemcpyAsync(residuals, d_res, sizeof(double) * B * n * 3, cudaMemcpyDeviceToHost, st));
+    if (vectors) DFDM_CUDA_OK(cudaMemcpyAsync(vectors, d_vec, sizeof(double) * B * E * 3, cudaMemcpyDeviceToHost, st));
+    if (lengths) DFDM_CUDA_OK(cudaMemcpyAsync(lengths, d_len, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
+    if (forces) DFDM_CUDA_OK(cudaMemcpyAsync(forces, d_for, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
+    if (status) DFDM_CUDA_OK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    DFDM_CUDA_OK(cudaStreamSynchronize(st));
+    return DFDM_OK;
+}
+
+int dfdm_forward_host(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
+                      double* xyz, double* residuals, double* vectors, double* lengths, double* forces, int32_t* status,
+                      const dfdm_options* options) {
+    return host_eval(plan, nullptr, batch, q, loads, xyz_fixed, nullptr, nullptr, xyz, residuals, vectors, lengths, forces, status,
+                     options);
+}
+
+int dfdm_loss_and_grad_host(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t batch, const double* q, const double* loads,
+                            const double* xyz_fixed, double* loss, double* dq, int32_t* status, const dfdm_options* options) {
+    if (!prog || !loss) {
+        set_error("dfdm_loss_and_grad_host: NULL goal program or loss buffer");
+        return DFDM_EINVAL;
+    }
+    return host_eval(plan, prog, batch, q, loads, xyz_fixed, loss, dq, nullptr, nullptr, nullptr, nullptr, nullptr, status, options);
+}
+
+int64_t dfdm_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters) {
+    int f = 0, a = 0;
+    last_pcg_iterations(&f, &a);
+    if (forward_iters) *forward_iters = f;
+    if (adjoint_iters) *adjoint_iters = a;
+}
+
+}  // extern "C"

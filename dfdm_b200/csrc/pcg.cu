@@ -1,0 +1,759 @@
+// Large-network path: Jacobi-preconditioned CG on a batch-interleaved CSR, all designs in lock step.
+//
+// Layout: every per-design array is stored element-major with the batch innermost, A[elem][B], so a
+// warp that works on one row / edge for 32 consecutive designs reads and writes 256 contiguous bytes
+// and index loads (rowptr, colidx, incidence) are warp-uniform broadcasts amortised over the batch.
+// For small batches the same kernels fold several rows into a warp (lanes = rows x designs).
+//
+// CTA decomposition used by every kernel here: blockIdx -> (batch chunk, slab); a thread owns one
+// design lane b and walks rows slab*rstep + rl, += nslabs*rstep, so that all resident CTAs sweep the
+// row range together (neighbour rows x[col] are then served by L1/L2, each vector is read from HBM
+// once per pass).  Per-design dot products are reduced in a fixed order: registers -> shared memory
+// -> one partial per (slab, design) -> the last CTA of each chunk sums the slabs.  No atomics on data.
+//
+// Reference being replaced: np.linalg.solve in src/dfdm/equilibrium/model.py:55 (for networks whose
+// banded factor does not fit shared memory) plus the assembly of model.py:50-54 and the
+// post-processing of model.py:21-34, batched.
+#include "common.cuh"
+
+namespace dfdm {
+
+struct LaneCfg {
+    int shift;     // design lanes per CTA row group = 1 << shift (<= 32)
+    int nchunks;   // ceil(B / lanes)
+    int nslabs;    // CTAs per chunk
+    int rstep;     // rows handled per CTA iteration = blockDim / lanes
+};
+
+constexpr int kThreads = 256;
+
+#define LANE_SETUP()                                                        \
+    const int cbl = 1 << cfg.shift;                                         \
+    const int chunk = blockIdx.x % cfg.nchunks;                             \
+    const int slab = blockIdx.x / cfg.nchunks;                              \
+    const int bl = threadIdx.x & (cbl - 1);                                 \
+    const int rl = threadIdx.x >> cfg.shift;                                \
+    const int b = chunk * cbl + bl;                                         \
+    const bool live = b < B;                                                \
+    const int row0 = slab * cfg.rstep + rl;                                 \
+    const int rstride = cfg.nslabs * cfg.rstep;                             \
+    (void)live; (void)row0; (void)rstride; (void)chunk; (void)slab; (void)bl; (void)rl;
+
+// Per-design scalars of the solver, each [3][B] unless noted.
+struct PcgScalars {
+    double* rho;      // r . z
+    double* alpha;
+    double* beta;
+    double* bb;       // ||b||^2
+    int32_t* frozen;  // [3][B] converged (or zero right-hand side): alpha forced to 0
+    int32_t* n_active;   // [0] columns not yet converged (live); [1] snapshot taken between iterations, read by the early exits
+    int32_t* tickets;    // [nchunks]
+    double* partial;     // [nslabs][NV][B] scratch for block partials
+};
+
+// Reduce NV per-thread values over the rows of this CTA and publish one partial per (slab, design).
+// Returns true in the CTA that arrived last for its chunk (all partials of the chunk are then visible).
+template <int NV>
+__device__ bool publish_partials(double (&v)[NV], const LaneCfg& cfg, int B, double* partial, int32_t* tickets) {
+    __shared__ double red[NV][kThreads];
+    __shared__ int s_last;
+    LANE_SETUP();
+#pragma unroll
+    for (int c = 0; c < NV; ++c) red[c][threadIdx.x] = v[c];
+    __syncthreads();
+    if (rl == 0 && live) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            double s = 0.0;
+            for (int r = 0; r < cfg.rstep; ++r) s += red[c][(r << cfg.shift) + bl];
+            partial[((size_t)slab * NV + c) * B + b] = s;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = atomicAdd(&tickets[chunk], 1);
+        s_last = (t == cfg.nslabs - 1);
+        if (s_last) tickets[chunk] = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+template <int NV>
+__device__ __forceinline__ double sum_slabs(const double* partial, int c, int b, int B, int nslabs) {
+    double s = 0.0;
+    for (int sl = 0; sl < nslabs; ++sl) s += __ldcg(&partial[((size_t)sl * NV + c) * B + b]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout changes
+// ------------------------------------------------------------------------------------------------
+
+// src[B][rows] -> dst[rows][B]
+__global__ void k_to_interleaved(const double* __restrict__ src, double* __restrict__ dst, int B, int rows) {
+    __shared__ double tile[32][33];
+    int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int b = b0 + j, r = r0 + threadIdx.x;
+        if (b < B && r < rows) tile[j][threadIdx.x] = src[(size_t)b * rows + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j, b = b0 + threadIdx.x;
+        if (b < B && r < rows) dst[(size_t)r * B + b] = tile[threadIdx.x][j];
+    }
+}
+
+// src[rows][B] -> dst[B][rows]
+__global__ void k_to_design_major(const double* __restrict__ src, double* __restrict__ dst, int B, int rows) {
+    __shared__ double tile[32][33];
+    int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j, b = b0 + threadIdx.x;
+        if (b < B && r < rows) tile[j][threadIdx.x] = src[(size_t)r * B + b];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int b = b0 + j, r = r0 + threadIdx.x;
+        if (b < B && r < rows) dst[(size_t)b * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly: K values (CSR, interleaved), Jacobi inverse, load term
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads) k_assemble(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ qT,
+                                                      const double* __restrict__ loads, const double* __restrict__ xfix,
+                                                      double* __restrict__ vals, double* __restrict__ dinv, double* __restrict__ rhs) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int f = row0; f < P.nf; f += rstride) {
+        int node = P.free_nodes[f];
+        double diag = 0.0;
+        double r0 = loads[node * 3 + 0], r1 = loads[node * 3 + 1], r2 = loads[node * 3 + 2];
+        int k0 = P.finc_ptr[f], k1 = P.finc_ptr[f + 1];
+        int prev = -1;
+        double acc = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            double qe = qT[(size_t)P.finc_edge[k] * B + b];
+            int code = P.finc_code[k];
+            diag += qe;
+            if (code >= 0) {
+                // entries of one row are grouped by slot only for multi-edges; accumulate through memory then
+                if (code == prev) acc += -qe; else acc = -qe;
+                vals[(size_t)code * B + b] = acc;
+                prev = code;
+            } else {
+                const double* xk = xfix + (size_t)(-1 - code) * 3;
+                r0 += qe * xk[0];
+                r1 += qe * xk[1];
+                r2 += qe * xk[2];
+            }
+        }
+        vals[(size_t)P.diagslot[f] * B + b] = diag;
+        dinv[(size_t)f * B + b] = 1.0 / diag;
+        rhs[((size_t)f * 3 + 0) * B + b] = r0;
+        rhs[((size_t)f * 3 + 1) * B + b] = r1;
+        rhs[((size_t)f * 3 + 2) * B + b] = r2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PCG kernels.  Vectors x, r, p, Ap are [nf][3][B].
+// ------------------------------------------------------------------------------------------------
+
+// x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
+__global__ void __launch_bounds__(kThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                      const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
+                                                      PcgScalars S) {
+    LANE_SETUP();
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (live) {
+        for (int f = row0; f < nf; f += rstride) {
+            double di = dinv[(size_t)f * B + b];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                size_t o = ((size_t)f * 3 + c) * B + b;
+                double rc = r[o];
+                double z = rc * di;
+                x[o] = 0.0;
+                p[o] = z;
+                v[c] += rc * z;
+                v[3 + c] += rc * rc;
+            }
+        }
+    }
+    if (publish_partials<6>(v, cfg, B, S.partial, S.tickets)) {
+        int fresh = 0;
+        for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
+            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            if (b2 >= B) continue;
+            double rho = sum_slabs<6>(S.partial, c, b2, B, cfg.nslabs);
+            double bb = sum_slabs<6>(S.partial, 3 + c, b2, B, cfg.nslabs);
+            S.rho[c * B + b2] = rho;
+            S.bb[c * B + b2] = bb;
+            S.beta[c * B + b2] = 0.0;
+            int frozen = (bb == 0.0 || !(rho != 0.0)) ? 1 : 0;     // zero right-hand side: x = 0 is exact
+            S.frozen[c * B + b2] = frozen;
+            fresh += frozen ? 0 : 1;
+        }
+        if (fresh) atomicAdd(S.n_active, fresh);
+    }
+}
+
+// Ap = K p ; sigma = p . Ap ; alpha = rho / sigma
+__global__ void __launch_bounds__(kThreads) k_pcg_spmv(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ vals,
+                                                      const double* __restrict__ p, double* __restrict__ Ap, PcgScalars S) {
+    if (__ldcg(&S.n_active[1]) == 0) return;
+    LANE_SETUP();
+    double v[3] = {0, 0, 0};
+    if (live) {
+        for (int f = row0; f < P.nf; f += rstride) {
+            int k0 = P.rowptr[f], k1 = P.rowptr[f + 1];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int k = k0; k < k1; ++k) {
+                double a = vals[(size_t)k * B + b];
+                size_t o = (size_t)P.colidx[k] * 3 * B + b;
+                a0 += a * p[o];
+                a1 += a * p[o + B];
+                a2 += a * p[o + 2 * (size_t)B];
+            }
+            size_t o = (size_t)f * 3 * B + b;
+            Ap[o] = a0;
+            Ap[o + B] = a1;
+            Ap[o + 2 * (size_t)B] = a2;
+            v[0] += p[o] * a0;
+            v[1] += p[o + B] * a1;
+            v[2] += p[o + 2 * (size_t)B] * a2;
+        }
+    }
+    if (publish_partials<3>(v, cfg, B, S.partial, S.tickets)) {
+        for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
+            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            if (b2 >= B) continue;
+            double sigma = sum_slabs<3>(S.partial, c, b2, B, cfg.nslabs);
+            double al = 0.0;
+            if (!S.frozen[c * B + b2] && sigma != 0.0) al = S.rho[c * B + b2] / sigma;
+            if (!isfinite(al)) al = 0.0;
+            S.alpha[c * B + b2] = al;
+        }
+    }
+}
+
+// x += alpha p ; r -= alpha Ap ; rho' = r . (r/diag) ; rr = r.r ; beta = rho'/rho ; convergence
+__global__ void __launch_bounds__(kThreads) k_pcg_update(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                        const double* __restrict__ p, const double* __restrict__ Ap,
+                                                        double* __restrict__ x, double* __restrict__ r, PcgScalars S, double tol2) {
+    // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
+    if (__ldcg(&S.n_active[1]) == 0) return;
+    LANE_SETUP();
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (live) {
+        double al[3] = {__ldcg(&S.alpha[b]), __ldcg(&S.alpha[B + b]), __ldcg(&S.alpha[2 * B + b])};
+        for (int f = row0; f < nf; f += rstride) {
+            double di = dinv[(size_t)f * B + b];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                size_t o = ((size_t)f * 3 + c) * B + b;
+                double pc = p[o], ac = Ap[o];
+                x[o] += al[c] * pc;
+                double rc = r[o] - al[c] * ac;
+                r[o] = rc;
+                v[c] += rc * rc * di;
+                v[3 + c] += rc * rc;
+            }
+        }
+    }
+    if (publish_partials<6>(v, cfg, B, S.partial, S.tickets)) {
+        int done = 0;
+        for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
+            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            if (b2 >= B) continue;
+            int o = c * B + b2;
+            if (S.frozen[o]) { S.beta[o] = 0.0; continue; }
+            double rho_new = sum_slabs<6>(S.partial, c, b2, B, cfg.nslabs);
+            double rr = sum_slabs<6>(S.partial, 3 + c, b2, B, cfg.nslabs);
+            double rho_old = S.rho[o];
+            double be = rho_old != 0.0 ? rho_new / rho_old : 0.0;
+            if (!isfinite(be)) be = 0.0;
+            S.beta[o] = be;
+            S.rho[o] = rho_new;
+            if (!isfinite(rr)) {
+                S.frozen[o] = 2;                 // breakdown: reported as DFDM_STATUS_NONFINITE
+                done += 1;
+            } else if (rr <= tol2 * S.bb[o]) {
+                S.frozen[o] = 1;
+                done += 1;
+            }
+        }
+        if (done) atomicSub(S.n_active, done);
+    }
+}
+
+// p = r / diag + beta p
+__global__ void __launch_bounds__(kThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                           const double* __restrict__ r, double* __restrict__ p, PcgScalars S) {
+    if (__ldcg(&S.n_active[1]) == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1] = __ldcg(&S.n_active[0]);   // p is dead once everything converged
+    LANE_SETUP();
+    if (!live) return;
+    double be[3] = {__ldcg(&S.beta[b]), __ldcg(&S.beta[B + b]), __ldcg(&S.beta[2 * B + b])};
+    for (int f = row0; f < nf; f += rstride) {
+        double di = dinv[(size_t)f * B + b];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            size_t o = ((size_t)f * 3 + c) * B + b;
+            p[o] = r[o] * di + be[c] * p[o];
+        }
+    }
+}
+
+// status: not converged if any coordinate of the design is still active
+__global__ void k_pcg_status(int B, const int32_t* __restrict__ frozen, int32_t* __restrict__ status, int accumulate) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int f0 = frozen[b], f1 = frozen[B + b], f2 = frozen[2 * B + b];
+    int now = (f0 == 2 || f1 == 2 || f2 == 2) ? DFDM_STATUS_NONFINITE
+            : ((f0 && f1 && f2) ? DFDM_STATUS_OK : DFDM_STATUS_NOT_CONVERGED);
+    int prev = accumulate ? status[b] : DFDM_STATUS_OK;
+    status[b] = prev != DFDM_STATUS_OK ? prev : now;
+}
+
+// ------------------------------------------------------------------------------------------------
+// equilibrium state, goals, reverse pass (interleaved layout)
+// ------------------------------------------------------------------------------------------------
+
+// X[n][3][B] from the solution (free rows) and the supports
+__global__ void __launch_bounds__(kThreads) k_positions(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ xs,
+                                                       const double* __restrict__ xfix, double* __restrict__ X) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int i = row0; i < P.n; i += rstride) {
+        int src = P.node_src[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            X[((size_t)i * 3 + c) * B + b] = src >= 0 ? xs[((size_t)src * 3 + c) * B + b] : xfix[(size_t)(-1 - src) * 3 + c];
+    }
+}
+
+// U = C X, L = |U|, F = q L; per-slab partial of the load path sum |L F|
+__global__ void __launch_bounds__(kThreads) k_edge_state(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ qT,
+                                                        const double* __restrict__ X, double* __restrict__ U, double* __restrict__ Lg,
+                                                        double* __restrict__ F, double* __restrict__ lp_partial) {
+    LANE_SETUP();
+    double lp = 0.0;
+    if (live) {
+        for (int e = row0; e < P.E; e += rstride) {
+            int u = P.edges[2 * e], v = P.edges[2 * e + 1];
+            double d[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = X[((size_t)v * 3 + c) * B + b] - X[((size_t)u * 3 + c) * B + b];
+            double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            double f = qT[(size_t)e * B + b] * len;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) U[((size_t)e * 3 + c) * B + b] = d[c];
+            Lg[(size_t)e * B + b] = len;
+            F[(size_t)e * B + b] = f;
+            lp += fabs(len * f);
+        }
+    }
+    if (lp_partial) {
+        __shared__ double red[kThreads];
+        red[threadIdx.x] = lp;
+        __syncthreads();
+        if (rl == 0 && live) {
+            double s = 0.0;
+            for (int r = 0; r < cfg.rstep; ++r) s += red[(r << cfg.shift) + bl];
+            lp_partial[(size_t)slab * B + b] = s;
+        }
+    }
+}
+
+// R = P - C^T diag(q) U; node goals -> loss partial and direct cotangents of X and R
+__global__ void __launch_bounds__(kThreads) k_node_state(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
+                                                        const double* __restrict__ qT, const double* __restrict__ loads,
+                                                        const double* __restrict__ X, const double* __restrict__ U,
+                                                        double* __restrict__ R, double* __restrict__ Xb, double* __restrict__ Rb,
+                                                        const double* __restrict__ cX, const double* __restrict__ cR,
+                                                        double* __restrict__ loss_partial) {
+    LANE_SETUP();
+    double loss = 0.0;
+    if (live) {
+        for (int i = row0; i < P.n; i += rstride) {
+            double r[3] = {loads[i * 3 + 0], loads[i * 3 + 1], loads[i * 3 + 2]};
+            for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
+                int e = P.ninc_edge[k];
+                double s = (double)P.ninc_sign[k] * qT[(size_t)e * B + b];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) r[c] -= s * U[((size_t)e * 3 + c) * B + b];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[((size_t)i * 3 + c) * B + b] = r[c];
+            if (has_prog || seeds) {
+                double xb[3] = {0, 0, 0}, rb[3] = {0, 0, 0};
+                if (has_prog) {
+                    int g0 = G.ngoal_ptr[i], g1 = G.ngoal_ptr[i + 1];
+                    if (g1 > g0) {
+                        double x[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) x[c] = X[((size_t)i * 3 + c) * B + b];
+                        loss += node_goals(G.recs, g0, g1, x, r, xb, rb);
+                    }
+                }
+                if (seeds) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        size_t o = ((size_t)i * 3 + c) * B + b;
+                        if (cX) xb[c] += cX[o];
+                        if (cR) rb[c] += cR[o];
+                        Xb[o] = xb[c];
+                        Rb[o] = rb[c];
+                    }
+                }
+            }
+        }
+    }
+    if (loss_partial) {
+        __shared__ double red[kThreads];
+        red[threadIdx.x] = loss;
+        __syncthreads();
+        if (rl == 0 && live) {
+            double s = 0.0;
+            for (int r = 0; r < cfg.rstep; ++r) s += red[(r << cfg.shift) + bl];
+            loss_partial[(size_t)slab * B + b] = s;
+        }
+    }
+}
+
+// total load path and the network goals: lpbar[B] = d loss / d loadpath, net_loss[B]
+__global__ void k_network_goals(GoalProgDev G, int B, int nslabs, const double* __restrict__ lp_partial, double* __restrict__ lpbar,
+                                double* __restrict__ net_loss) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double lp = 0.0;
+    for (int s = 0; s < nslabs; ++s) lp += lp_partial[(size_t)s * B + b];
+    double bar;
+    net_loss[b] = network_goals(G.recs, G.net_begin, G.net_begin + G.n_net, lp, bar);
+    lpbar[b] = bar;
+}
+
+// edge goals + reverse steps 1-3: Ub (total cotangent of U), partial dq
+__global__ void __launch_bounds__(kThreads) k_edge_adjoint(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
+                                                          const double* __restrict__ qT, const double* __restrict__ U,
+                                                          const double* __restrict__ Lg, const double* __restrict__ F,
+                                                          const double* __restrict__ Rb, const double* __restrict__ lpbar,
+                                                          const double* __restrict__ cU, const double* __restrict__ cL,
+                                                          const double* __restrict__ cF, double* __restrict__ Ub,
+                                                          double* __restrict__ dqT, double* __restrict__ loss_partial) {
+    LANE_SETUP();
+    double loss = 0.0;
+    if (live) {
+        double lpb = (has_prog && G.n_net > 0) ? lpbar[b] : 0.0;
+        for (int e = row0; e < P.E; e += rstride) {
+            double u[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = U[((size_t)e * 3 + c) * B + b];
+            double len = Lg[(size_t)e * B + b], f = F[(size_t)e * B + b], qe = qT[(size_t)e * B + b];
+            double ub[3] = {0, 0, 0}, lb = 0.0, fb = 0.0;
+            if (has_prog) {
+                int g0 = G.egoal_ptr[e], g1 = G.egoal_ptr[e + 1];
+                if (g1 > g0) loss += edge_goals(G.recs, g0, g1, u, len, f, ub, lb, fb);
+                loss += G.l2_alpha * qe * qe;
+            }
+            if (seeds) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (cU) ub[c] += cU[((size_t)e * 3 + c) * B + b];
+                if (cL) lb += cL[(size_t)e * B + b];
+                if (cF) fb += cF[(size_t)e * B + b];
+                int un = P.edges[2 * e], vn = P.edges[2 * e + 1];
+                double g[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c] = Rb[((size_t)vn * 3 + c) * B + b] - Rb[((size_t)un * 3 + c) * B + b];
+                double d = edge_adjoint(qe, u, len, f, g, lpb, ub, lb, fb);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Ub[((size_t)e * 3 + c) * B + b] = ub[c];
+                dqT[(size_t)e * B + b] = d + 2.0 * G.l2_alpha * qe;
+            }
+        }
+    }
+    if (loss_partial) {
+        __shared__ double red[kThreads];
+        red[threadIdx.x] = loss;
+        __syncthreads();
+        if (rl == 0 && live) {
+            double s = 0.0;
+            for (int r = 0; r < cfg.rstep; ++r) s += red[(r << cfg.shift) + bl];
+            loss_partial[(size_t)slab * B + b] = s;
+        }
+    }
+}
+
+// right-hand side of the adjoint solve: (Xb + C^T Ub) on the free rows
+__global__ void __launch_bounds__(kThreads) k_adjoint_rhs(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ Xb,
+                                                         const double* __restrict__ Ub, double* __restrict__ rhs) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int f = row0; f < P.nf; f += rstride) {
+        int i = P.free_nodes[f];
+        double xb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xb[c] = Xb[((size_t)i * 3 + c) * B + b];
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
+            int e = P.ninc_edge[k];
+            double s = (double)P.ninc_sign[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xb[c] += s * Ub[((size_t)e * 3 + c) * B + b];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rhs[((size_t)f * 3 + c) * B + b] = xb[c];
+    }
+}
+
+// dq -= (C_f lambda)_e . U_e
+__global__ void __launch_bounds__(kThreads) k_edge_dq(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ lam,
+                                                     const double* __restrict__ U, double* __restrict__ dqT) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int e = row0; e < P.E; e += rstride) {
+        int su = P.node_src[P.edges[2 * e]], sv = P.node_src[P.edges[2 * e + 1]];
+        double d = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double lv = sv >= 0 ? lam[((size_t)sv * 3 + c) * B + b] : 0.0;
+            double lu = su >= 0 ? lam[((size_t)su * 3 + c) * B + b] : 0.0;
+            d += (lv - lu) * U[((size_t)e * 3 + c) * B + b];
+        }
+        dqT[(size_t)e * B + b] -= d;
+    }
+}
+
+// loss[b] = sum of the slab partials (+ network goal loss)
+__global__ void k_loss_final(int B, int nslabs, const double* __restrict__ pn, const double* __restrict__ pe,
+                             const double* __restrict__ net_loss, double* __restrict__ loss) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int k = 0; k < nslabs; ++k) s += pn[(size_t)k * B + b];
+    for (int k = 0; k < nslabs; ++k) s += pe[(size_t)k * B + b];
+    if (net_loss) s += net_loss[b];
+    loss[b] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+
+static thread_local int g_iters[2] = {0, 0};
+void last_pcg_iterations(int* fwd, int* adj) {
+    if (fwd) *fwd = g_iters[0];
+    if (adj) *adj = g_iters[1];
+}
+
+static int lane_config(int B, LaneCfg& cfg, int max_rows) {
+    int shift = 0;
+    while ((1 << shift) < B && shift < 5) ++shift;
+    cfg.shift = shift;
+    int cbl = 1 << shift;
+    cfg.nchunks = (B + cbl - 1) / cbl;
+    cfg.rstep = kThreads / cbl;
+    int dev = 0, sms = 0;
+    DFDM_CUDA_OK(cudaGetDevice(&dev));
+    DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int resident = sms * 6;                                  // 256-thread CTAs at <= 40 registers
+    int want = (resident + cfg.nchunks - 1) / cfg.nchunks;
+    int most = (max_rows + cfg.rstep - 1) / cfg.rstep;
+    cfg.nslabs = std::max(1, std::min(want, most));
+    return DFDM_OK;
+}
+
+struct PcgBuffers {
+    double *qT, *vals, *dinv, *xs, *r, *p, *Ap;
+    double *X, *R, *U, *L, *F, *Xb, *Rb, *Ub, *dqT;
+    double *cX, *cR, *cU, *cL, *cF;
+    double *lp_partial, *pn, *pe, *lpbar, *net_loss;
+    PcgScalars S;
+    int32_t* host_flag;   // pinned
+};
+
+static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int64_t B, int nslabs_max,
+                  int nchunks_max, PcgBuffers& w) {
+    w.qT = bump.take<double>(E * B);
+    w.vals = bump.take<double>(nnz * B);
+    w.dinv = bump.take<double>(nf * B);
+    w.xs = bump.take<double>(nf * 3 * B);
+    w.r = bump.take<double>(nf * 3 * B);
+    w.p = bump.take<double>(nf * 3 * B);
+    w.Ap = bump.take<double>(nf * 3 * B);
+    w.X = bump.take<double>(n * 3 * B);
+    w.R = bump.take<double>(n * 3 * B);
+    w.U = bump.take<double>(E * 3 * B);
+    w.L = bump.take<double>(E * B);
+    w.F = bump.take<double>(E * B);
+    w.Xb = bump.take<double>(n * 3 * B);
+    w.Rb = bump.take<double>(n * 3 * B);
+    w.Ub = bump.take<double>(E * 3 * B);
+    w.dqT = bump.take<double>(E * B);
+    w.cX = bump.take<double>(n * 3 * B);
+    w.cR = bump.take<double>(n * 3 * B);
+    w.cU = bump.take<double>(E * 3 * B);
+    w.cL = bump.take<double>(E * B);
+    w.cF = bump.take<double>(E * B);
+    w.lp_partial = bump.take<double>((int64_t)nslabs_max * B);
+    w.pn = bump.take<double>((int64_t)nslabs_max * B);
+    w.pe = bump.take<double>((int64_t)nslabs_max * B);
+    w.lpbar = bump.take<double>(B);
+    w.net_loss = bump.take<double>(B);
+    w.S.rho = bump.take<double>(3 * B);
+    w.S.alpha = bump.take<double>(3 * B);
+    w.S.beta = bump.take<double>(3 * B);
+    w.S.bb = bump.take<double>(3 * B);
+    w.S.partial = bump.take<double>((int64_t)nslabs_max * 6 * B);
+    w.S.frozen = bump.take<int32_t>(3 * B);
+    w.S.n_active = bump.take<int32_t>(64);
+    w.S.tickets = bump.take<int32_t>(nchunks_max + 64);
+}
+
+// upper bounds that do not depend on the device: nslabs <= 148 * 6 would need the device; use a generous cap
+static constexpr int kMaxSlabs = 2048;
+
+int64_t pcg_workspace(const Plan& P, int B) {
+    Bump bump(nullptr);
+    PcgBuffers w{};
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w);
+    return bump.off;
+}
+
+static int pcg_solve(const PlanDev& P, const LaneCfg& cfg, int B, PcgBuffers& w, const dfdm_options& opt, cudaStream_t st,
+                     int32_t* host_flag, int* iters_out) {
+    int grid = cfg.nchunks * cfg.nslabs;
+    int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
+    double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
+    int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : 25;
+    DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
+    DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, sizeof(int32_t), st));      // snapshot: non-zero
+    k_pcg_init<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S);
+    DFDM_LAUNCH_OK("k_pcg_init");
+    int it = 0;
+    while (it < maxiter) {
+        int stop = std::min(maxiter, it + every);
+        for (; it < stop; ++it) {
+            k_pcg_spmv<<<grid, kThreads, 0, st>>>(P, cfg, B, w.vals, w.p, w.Ap, w.S);
+            DFDM_LAUNCH_OK("k_pcg_spmv");
+            k_pcg_update<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S, rtol * rtol);
+            DFDM_LAUNCH_OK("k_pcg_update");
+            k_pcg_direction<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.p, w.S);
+            DFDM_LAUNCH_OK("k_pcg_direction");
+        }
+        DFDM_CUDA_OK(cudaMemcpyAsync(host_flag, w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        DFDM_CUDA_OK(cudaStreamSynchronize(st));
+        if (*host_flag == 0) break;
+    }
+    *iters_out = it;
+    return DFDM_OK;
+}
+
+static int to_interleaved(const double* src, double* dst, int B, int64_t rows, cudaStream_t st) {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((B + 31) / 32)), block(32, 8);
+    k_to_interleaved<<<grid, block, 0, st>>>(src, dst, B, (int)rows);
+    DFDM_LAUNCH_OK("k_to_interleaved");
+    return DFDM_OK;
+}
+
+static int to_design_major(const double* src, double* dst, int B, int64_t rows, cudaStream_t st) {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((B + 31) / 32)), block(32, 8);
+    k_to_design_major<<<grid, block, 0, st>>>(src, dst, B, (int)rows);
+    DFDM_LAUNCH_OK("k_to_design_major");
+    return DFDM_OK;
+}
+
+int run_pcg(Eval& ev) {
+    const PlanDev& P = ev.P;
+    const int B = ev.B;
+    cudaStream_t st = ev.stream;
+    LaneCfg cfg{};
+    int rc = lane_config(B, cfg, std::max(P.E, P.n));
+    if (rc) return rc;
+    if (cfg.nslabs > kMaxSlabs) cfg.nslabs = kMaxSlabs;
+    Bump bump(ev.ws);
+    PcgBuffers w{};
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w);
+    if (bump.off > ev.ws_bytes) {
+        set_error("workspace too small for the PCG path: need " + std::to_string(bump.off) + " bytes");
+        return DFDM_ENOMEM;
+    }
+    static thread_local int32_t* host_flag = nullptr;
+    if (!host_flag) DFDM_CUDA_OK(cudaMallocHost(&host_flag, 64));
+    const int grid = cfg.nchunks * cfg.nslabs;
+    const int tb = 128, gb = (B + tb - 1) / tb;
+
+    DFDM_CUDA_OK(cudaMemsetAsync(w.S.tickets, 0, sizeof(int32_t) * (size_t)(cfg.nchunks + 1), st));
+    rc = to_interleaved(ev.q, w.qT, B, P.E, st);
+    if (rc) return rc;
+    k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
+    DFDM_LAUNCH_OK("k_assemble");
+    g_iters[0] = g_iters[1] = 0;
+    rc = pcg_solve(P, cfg, B, w, ev.opt, st, host_flag, &g_iters[0]);
+    if (rc) return rc;
+    if (ev.status) {
+        k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 0);
+        DFDM_LAUNCH_OK("k_pcg_status");
+    }
+
+    const bool net = ev.has_prog && ev.G.n_net > 0;
+    const bool seeds = ev.adjoint;
+    k_positions<<<grid, kThreads, 0, st>>>(P, cfg, B, w.xs, ev.xfix, w.X);
+    DFDM_LAUNCH_OK("k_positions");
+    k_edge_state<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, w.X, w.U, w.L, w.F, net ? w.lp_partial : nullptr);
+    DFDM_LAUNCH_OK("k_edge_state");
+    const double *cX = nullptr, *cR = nullptr, *cU = nullptr, *cL = nullptr, *cF = nullptr;
+    if (seeds) {
+        if (ev.c_xyz) { rc = to_interleaved(ev.c_xyz, w.cX, B, (int64_t)P.n * 3, st); if (rc) return rc; cX = w.cX; }
+        if (ev.c_res) { rc = to_interleaved(ev.c_res, w.cR, B, (int64_t)P.n * 3, st); if (rc) return rc; cR = w.cR; }
+        if (ev.c_vec) { rc = to_interleaved(ev.c_vec, w.cU, B, (int64_t)P.E * 3, st); if (rc) return rc; cU = w.cU; }
+        if (ev.c_len) { rc = to_interleaved(ev.c_len, w.cL, B, P.E, st); if (rc) return rc; cL = w.cL; }
+        if (ev.c_for) { rc = to_interleaved(ev.c_for, w.cF, B, P.E, st); if (rc) return rc; cF = w.cF; }
+    }
+    k_node_state<<<grid, kThreads, 0, st>>>(P, ev.G, ev.has_prog ? 1 : 0, seeds ? 1 : 0, cfg, B, w.qT, ev.loads, w.X, w.U, w.R,
+                                           w.Xb, w.Rb, cX, cR, ev.loss ? w.pn : nullptr);
+    DFDM_LAUNCH_OK("k_node_state");
+    if (net) {
+        k_network_goals<<<gb, tb, 0, st>>>(ev.G, B, cfg.nslabs, w.lp_partial, w.lpbar, w.net_loss);
+        DFDM_LAUNCH_OK("k_network_goals");
+    }
+    if (ev.has_prog || seeds) {
+        k_edge_adjoint<<<grid, kThreads, 0, st>>>(P, ev.G, ev.has_prog ? 1 : 0, seeds ? 1 : 0, cfg, B, w.qT, w.U, w.L, w.F, w.Rb,
+                                                 w.lpbar, cU, cL, cF, w.Ub, w.dqT, ev.loss ? w.pe : nullptr);
+        DFDM_LAUNCH_OK("k_edge_adjoint");
+    }
+    if (ev.loss) {
+        k_loss_final<<<gb, tb, 0, st>>>(B, cfg.nslabs, w.pn, w.pe, net ? w.net_loss : nullptr, ev.loss);
+        DFDM_LAUNCH_OK("k_loss_final");
+    }
+    if (seeds) {
+        k_adjoint_rhs<<<grid, kThreads, 0, st>>>(P, cfg, B, w.Xb, w.Ub, w.r);
+        DFDM_LAUNCH_OK("k_adjoint_rhs");
+        rc = pcg_solve(P, cfg, B, w, ev.opt, st, host_flag, &g_iters[1]);
+        if (rc) return rc;
+        if (ev.status) {
+            k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 1);
+            DFDM_LAUNCH_OK("k_pcg_status");
+        }
+        k_edge_dq<<<grid, kThreads, 0, st>>>(P, cfg, B, w.xs, w.U, w.dqT);
+        DFDM_LAUNCH_OK("k_edge_dq");
+        rc = to_design_major(w.dqT, ev.dq, B, P.E, st);
+        if (rc) return rc;
+    }
+    if (ev.o_xyz) { rc = to_design_major(w.X, ev.o_xyz, B, (int64_t)P.n * 3, st); if (rc) return rc; }
+    if (ev.o_res) { rc = to_design_major(w.R, ev.o_res, B, (int64_t)P.n * 3, st); if (rc) return rc; }
+    if (ev.o_vec) { rc = to_design_major(w.U, ev.o_vec, B, (int64_t)P.E * 3, st); if (rc) return rc; }
+    if (ev.o_len) { rc = to_design_major(w.L, ev.o_len, B, P.E, st); if (rc) return rc; }
+    if (ev.o_for) { rc = to_design_major(w.F, ev.o_for, B, P.E, st); if (rc) return rc; }
+    return DFDM_OK;
+}
+
+}  // namespace dfdm

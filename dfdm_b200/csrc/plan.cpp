@@ -1,0 +1,324 @@
+// Topology compiler: integer preprocessing done once per network.
+//
+// Replaces what the reference recomputes on every evaluation (src/dfdm/equilibrium/model.py:44-47:
+// column slices of the dense branch-node matrix) and what it builds per model
+// (src/dfdm/equilibrium/structure.py:63-106).  Everything here must be bit-exact with respect to the
+// reference's indexing: free / fixed lists ascending, freefixed = position of each node in
+// [free; fixed], C[e,u] = -1, C[e,v] = +1.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <queue>
+
+namespace dfdm {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+
+// Reverse Cuthill-McKee over the free-node graph given as CSR (diagonal entries ignored).
+static void rcm_order(int nf, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx,
+                      std::vector<int32_t>& perm) {
+    perm.clear();
+    perm.reserve(nf);
+    std::vector<int32_t> degree(nf), level(nf, -1);
+    std::vector<char> visited(nf, 0);
+    for (int i = 0; i < nf; ++i) degree[i] = rowptr[i + 1] - rowptr[i] - 1;
+
+    auto bfs_far = [&](int start, std::vector<int32_t>& order) {
+        // plain BFS; returns the visiting order, fills level[] for the component
+        order.clear();
+        order.push_back(start);
+        level[start] = 0;
+        for (size_t head = 0; head < order.size(); ++head) {
+            int i = order[head];
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                int j = colidx[k];
+                if (j != i && level[j] < 0) {
+                    level[j] = level[i] + 1;
+                    order.push_back(j);
+                }
+            }
+        }
+    };
+
+    std::vector<int32_t> comp, nbrs;
+    for (int seed = 0; seed < nf; ++seed) {
+        if (visited[seed]) continue;
+        // pseudo-peripheral start: iterate BFS from the farthest, lowest-degree node
+        int start = seed;
+        bfs_far(start, comp);
+        for (int it = 0; it < 8; ++it) {
+            int depth = level[comp.back()];
+            int best = comp.back();
+            for (int idx = (int)comp.size() - 1; idx >= 0 && level[comp[idx]] == depth; --idx)
+                if (degree[comp[idx]] < degree[best] || (degree[comp[idx]] == degree[best] && comp[idx] < best)) best = comp[idx];
+            for (int i : comp) level[i] = -1;
+            std::vector<int32_t> trial;
+            bfs_far(best, trial);
+            int new_depth = level[trial.back()];
+            if (new_depth > depth) {
+                start = best;
+                comp.swap(trial);
+            } else {
+                for (int i : trial) level[i] = -1;
+                bfs_far(start, comp);
+                break;
+            }
+        }
+        for (int i : comp) level[i] = -1;
+        // Cuthill-McKee from `start`: neighbours by ascending degree, ties by index
+        size_t begin = perm.size();
+        perm.push_back(start);
+        visited[start] = 1;
+        for (size_t head = begin; head < perm.size(); ++head) {
+            int i = perm[head];
+            nbrs.clear();
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                int j = colidx[k];
+                if (j != i && !visited[j]) {
+                    visited[j] = 1;
+                    nbrs.push_back(j);
+                }
+            }
+            std::sort(nbrs.begin(), nbrs.end(), [&](int a, int b) { return degree[a] != degree[b] ? degree[a] < degree[b] : a < b; });
+            perm.insert(perm.end(), nbrs.begin(), nbrs.end());
+        }
+        std::reverse(perm.begin() + begin, perm.end());
+    }
+}
+
+static int bandwidth(int nf, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx,
+                     const std::vector<int32_t>& pos) {
+    int w = 0;
+    for (int i = 0; i < nf; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) w = std::max(w, std::abs(pos[i] - pos[colidx[k]]));
+    return w;
+}
+
+int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fixed, Plan& P) {
+    if (n <= 0 || E < 0 || (E > 0 && !edges) || !is_fixed) {
+        set_error("dfdm_plan_create: n must be positive and edges / is_fixed non-NULL");
+        return DFDM_EINVAL;
+    }
+    for (int e = 0; e < E; ++e) {
+        int u = edges[2 * e], v = edges[2 * e + 1];
+        if (u < 0 || u >= n || v < 0 || v >= n) {
+            set_error("dfdm_plan_create: edge " + std::to_string(e) + " references a node outside [0, n)");
+            return DFDM_EINVAL;
+        }
+    }
+    P.n = n;
+    P.E = E;
+    P.edges.assign(edges, edges + 2 * (size_t)E);
+
+    // structure.py:74-106
+    P.node_src.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (is_fixed[i]) {
+            P.node_src[i] = -1 - (int)P.fixed_nodes.size();
+            P.fixed_nodes.push_back(i);
+        } else {
+            P.node_src[i] = (int)P.free_nodes.size();
+            P.free_nodes.push_back(i);
+        }
+    }
+    P.nf = (int)P.free_nodes.size();
+    P.nx = (int)P.fixed_nodes.size();
+    if (P.nf == 0) {
+        set_error("dfdm_plan_create: the network has no free node");
+        return DFDM_EINVAL;
+    }
+    P.freefixed.resize(n);
+    for (int i = 0; i < n; ++i) P.freefixed[i] = P.node_src[i] >= 0 ? P.node_src[i] : P.nf + (-1 - P.node_src[i]);
+
+    // node -> incident edges with C[e, node] (self-loops cancel in C and are skipped)
+    P.ninc_ptr.assign(n + 1, 0);
+    for (int e = 0; e < E; ++e) {
+        int u = edges[2 * e], v = edges[2 * e + 1];
+        if (u == v) continue;
+        P.ninc_ptr[u + 1]++;
+        P.ninc_ptr[v + 1]++;
+    }
+    for (int i = 0; i < n; ++i) P.ninc_ptr[i + 1] += P.ninc_ptr[i];
+    P.ninc_edge.resize(P.ninc_ptr[n]);
+    P.ninc_sign.resize(P.ninc_ptr[n]);
+    {
+        std::vector<int32_t> cursor(P.ninc_ptr.begin(), P.ninc_ptr.end() - 1);
+        for (int e = 0; e < E; ++e) {
+            int u = edges[2 * e], v = edges[2 * e + 1];
+            if (u == v) continue;
+            P.ninc_edge[cursor[u]] = e;
+            P.ninc_sign[cursor[u]++] = -1;
+            P.ninc_edge[cursor[v]] = e;
+            P.ninc_sign[cursor[v]++] = +1;
+        }
+    }
+
+    // CSR pattern of K = C_f^T Q C_f in free order
+    const int nf = P.nf;
+    P.rowptr.assign(nf + 1, 0);
+    std::vector<std::vector<int32_t>> cols(nf);
+    for (int f = 0; f < nf; ++f) {
+        int i = P.free_nodes[f];
+        auto& c = cols[f];
+        c.push_back(f);
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
+            int e = P.ninc_edge[k];
+            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
+            if (P.node_src[other] >= 0) c.push_back(P.node_src[other]);
+        }
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        P.rowptr[f + 1] = P.rowptr[f] + (int)c.size();
+    }
+    P.nnz = P.rowptr[nf];
+    P.colidx.resize(P.nnz);
+    P.diagslot.resize(nf);
+    for (int f = 0; f < nf; ++f) {
+        std::copy(cols[f].begin(), cols[f].end(), P.colidx.begin() + P.rowptr[f]);
+        P.diagslot[f] = P.rowptr[f] + (int)(std::lower_bound(cols[f].begin(), cols[f].end(), f) - cols[f].begin());
+    }
+    auto slot_of = [&](int row, int col) {
+        auto b = P.colidx.begin() + P.rowptr[row], e = P.colidx.begin() + P.rowptr[row + 1];
+        return (int)(std::lower_bound(b, e, col) - P.colidx.begin());
+    };
+
+    // per-edge scatter slots (uu, vv, uv, vu)
+    P.edge_slots.assign(4 * (size_t)E, -1);
+    for (int e = 0; e < E; ++e) {
+        int u = edges[2 * e], v = edges[2 * e + 1];
+        if (u == v) continue;
+        int fu = P.node_src[u], fv = P.node_src[v];
+        if (fu >= 0) P.edge_slots[4 * e + 0] = P.diagslot[fu];
+        if (fv >= 0) P.edge_slots[4 * e + 1] = P.diagslot[fv];
+        if (fu >= 0 && fv >= 0) {
+            P.edge_slots[4 * e + 2] = slot_of(fu, fv);
+            P.edge_slots[4 * e + 3] = slot_of(fv, fu);
+        }
+    }
+
+    // free-row incidence (gather form of the scatter-add: one segment per row, fixed order)
+    P.finc_ptr.assign(nf + 1, 0);
+    for (int f = 0; f < nf; ++f) {
+        int i = P.free_nodes[f];
+        P.finc_ptr[f + 1] = P.finc_ptr[f] + (P.ninc_ptr[i + 1] - P.ninc_ptr[i]);
+    }
+    P.finc_edge.resize(P.finc_ptr[nf]);
+    P.finc_code.resize(P.finc_ptr[nf]);
+    for (int f = 0; f < nf; ++f) {
+        int i = P.free_nodes[f];
+        int o = P.finc_ptr[f];
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k, ++o) {
+            int e = P.ninc_edge[k];
+            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
+            P.finc_edge[o] = e;
+            P.finc_code[o] = P.node_src[other] >= 0 ? slot_of(f, P.node_src[other]) : P.node_src[other];
+        }
+        // parallel edges share a slot: keep them adjacent (code, then edge index) so the row sums them in a fixed order
+        std::vector<std::pair<int32_t, int32_t>> seg;
+        for (int k = P.finc_ptr[f]; k < P.finc_ptr[f + 1]; ++k) seg.emplace_back(P.finc_code[k], P.finc_edge[k]);
+        std::sort(seg.begin(), seg.end());
+        for (int k = P.finc_ptr[f], t = 0; k < P.finc_ptr[f + 1]; ++k, ++t) {
+            P.finc_code[k] = seg[t].first;
+            P.finc_edge[k] = seg[t].second;
+        }
+    }
+
+    // ordering for the banded direct solver
+    std::vector<int32_t> ident(nf);
+    std::iota(ident.begin(), ident.end(), 0);
+    P.w_nat = bandwidth(nf, P.rowptr, P.colidx, ident);
+    std::vector<int32_t> rperm, rpos(nf);
+    rcm_order(nf, P.rowptr, P.colidx, rperm);
+    for (int p = 0; p < nf; ++p) rpos[rperm[p]] = p;
+    int w_rcm = bandwidth(nf, P.rowptr, P.colidx, rpos);
+    if (w_rcm < P.w_nat) {
+        P.use_rcm = true;
+        P.perm = rperm;
+        P.pos = rpos;
+        P.w = w_rcm;
+    } else {
+        P.perm = ident;
+        P.pos = ident;
+        P.w = P.w_nat;
+    }
+
+    // incidence by solver position with band offsets
+    P.sinc_ptr.assign(nf + 1, 0);
+    for (int p = 0; p < nf; ++p) {
+        int f = P.perm[p];
+        P.sinc_ptr[p + 1] = P.sinc_ptr[p] + (P.finc_ptr[f + 1] - P.finc_ptr[f]);
+    }
+    P.sinc_edge.resize(P.sinc_ptr[nf]);
+    P.sinc_code.resize(P.sinc_ptr[nf]);
+    for (int p = 0; p < nf; ++p) {
+        int f = P.perm[p];
+        int i = P.free_nodes[f];
+        int o = P.sinc_ptr[p];
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k, ++o) {
+            int e = P.ninc_edge[k];
+            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
+            P.sinc_edge[o] = e;
+            if (P.node_src[other] >= 0) {
+                int pj = P.pos[P.node_src[other]];
+                P.sinc_code[o] = pj < p ? p - pj : 0;
+            } else {
+                P.sinc_code[o] = P.node_src[other];
+            }
+        }
+    }
+    return DFDM_OK;
+}
+
+}  // namespace dfdm
+
+namespace dfdm { const char* get_error(); }
+
+extern "C" {
+
+const char* dfdm_last_error(void) { return dfdm::get_error(); }
+int32_t dfdm_abi_version(void) { return DFDM_ABI_VERSION; }
+
+int dfdm_plan_get_info(const dfdm_plan* plan, dfdm_plan_info* info) {
+    if (!plan || !info) {
+        dfdm::set_error("dfdm_plan_get_info: NULL argument");
+        return DFDM_EINVAL;
+    }
+    std::memset(info, 0, sizeof(*info));
+    info->n = plan->n;
+    info->n_edges = plan->E;
+    info->n_free = plan->nf;
+    info->n_fixed = plan->nx;
+    info->nnz = plan->nnz;
+    info->bandwidth_natural = plan->w_nat;
+    info->bandwidth_solver = plan->w;
+    info->direct_smem_bytes = dfdm::direct_smem_bytes(plan->nf, plan->w);
+    info->direct_fits = info->direct_smem_bytes <= dfdm::kDirectSmemLimit ? 1 : 0;
+    info->auto_solver = info->direct_fits ? DFDM_SOLVER_DIRECT : DFDM_SOLVER_PCG;
+    return DFDM_OK;
+}
+
+const int32_t* dfdm_plan_array(const dfdm_plan* plan, int32_t which, int64_t* length) {
+    if (!plan) return nullptr;
+    const std::vector<int32_t>* v = nullptr;
+    switch (which) {
+        case DFDM_ARR_FREE: v = &plan->free_nodes; break;
+        case DFDM_ARR_FIXED: v = &plan->fixed_nodes; break;
+        case DFDM_ARR_FREEFIXED: v = &plan->freefixed; break;
+        case DFDM_ARR_ROWPTR: v = &plan->rowptr; break;
+        case DFDM_ARR_COLIDX: v = &plan->colidx; break;
+        case DFDM_ARR_EDGE_SLOTS: v = &plan->edge_slots; break;
+        case DFDM_ARR_SOLVER_PERM: v = &plan->perm; break;
+        case DFDM_ARR_NODE_INC_PTR: v = &plan->ninc_ptr; break;
+        case DFDM_ARR_NODE_INC_EDGE: v = &plan->ninc_edge; break;
+        case DFDM_ARR_NODE_INC_SIGN: v = &plan->ninc_sign; break;
+        default: dfdm::set_error("dfdm_plan_array: unknown array id"); return nullptr;
+    }
+    if (length) *length = (int64_t)v->size();
+    return v->data();
+}
+
+}  // extern "C"

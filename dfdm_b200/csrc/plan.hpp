@@ -1,0 +1,107 @@
+// Internal representation of a compiled topology ("plan") and goal program.
+// Host side only builds index arrays; the device mirrors are plain int32 / double arrays.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dfdm_b200.h"
+
+namespace dfdm {
+
+// Device-resident view of a plan (pointers into one device allocation).
+struct PlanDev {
+    int n = 0, E = 0, nf = 0, nx = 0, nnz = 0, w = 0;
+    const int32_t* edges = nullptr;       // [E][2]
+    const int32_t* node_src = nullptr;    // [n]: free index f >= 0, or -1 - k for fixed index k
+    const int32_t* free_nodes = nullptr;  // [nf] node id of each free index
+    // CSR of K (free order, sorted columns)
+    const int32_t* rowptr = nullptr;      // [nf+1]
+    const int32_t* colidx = nullptr;      // [nnz]
+    const int32_t* diagslot = nullptr;    // [nf]
+    // free-row incidence in free order: entry -> (edge, code) with code = CSR slot of the off-diagonal
+    // (>= 0) or -1 - k when the neighbour is fixed node k (contributes to the right-hand side)
+    const int32_t* finc_ptr = nullptr;    // [nf+1]
+    const int32_t* finc_edge = nullptr;
+    const int32_t* finc_code = nullptr;
+    // node incidence (all nodes): C[e, node]
+    const int32_t* ninc_ptr = nullptr;    // [n+1]
+    const int32_t* ninc_edge = nullptr;
+    const int32_t* ninc_sign = nullptr;
+    // direct solver ordering: position p <-> free index
+    const int32_t* perm = nullptr;        // [nf] free index at position p
+    const int32_t* pos = nullptr;         // [nf] position of free index
+    // incidence by solver position: code = band offset p - p_nbr (> 0, lower band), 0 = upper (skip),
+    // -1 - k = fixed neighbour k
+    const int32_t* sinc_ptr = nullptr;    // [nf+1]
+    const int32_t* sinc_edge = nullptr;
+    const int32_t* sinc_code = nullptr;
+};
+
+struct Plan {
+    int n = 0, E = 0, nf = 0, nx = 0, nnz = 0, w_nat = 0, w = 0;
+    bool use_rcm = false;
+    std::vector<int32_t> edges, free_nodes, fixed_nodes, freefixed, node_src;
+    std::vector<int32_t> rowptr, colidx, diagslot, edge_slots;
+    std::vector<int32_t> finc_ptr, finc_edge, finc_code;
+    std::vector<int32_t> ninc_ptr, ninc_edge, ninc_sign;
+    std::vector<int32_t> perm, pos;
+    std::vector<int32_t> sinc_ptr, sinc_edge, sinc_code;
+
+    // lazily created device mirrors and cached arenas for the *_host entry points
+    mutable std::mutex mu;
+    mutable std::map<int, PlanDev> dev;
+    mutable std::map<int, void*> dev_block;
+    struct Arena { void* ptr = nullptr; int64_t bytes = 0; };
+    mutable std::map<int, Arena> arena;
+};
+
+// One goal, flattened.  mode 0: contributes scale * weight * (p - t)^2 per component;
+// mode 1 (PredictionError): contributes scale * p per component.
+struct GoalRec {
+    int32_t kind;
+    int32_t elem;
+    int32_t mode;
+    int32_t pad;
+    double scale;    // alpha of the term (divided by the entry count for MeanSquaredError)
+    double weight;
+    double p[DFDM_GOAL_NPARAMS];
+};
+
+struct GoalProgDev {
+    int n_goals = 0, n_net = 0;
+    const GoalRec* recs = nullptr;      // sorted: node goals by node, edge goals by edge, network goals
+    const int32_t* ngoal_ptr = nullptr; // [n+1] into recs
+    const int32_t* egoal_ptr = nullptr; // [E+1] into recs (absolute indices)
+    int net_begin = 0;                  // network goals: recs[net_begin .. net_begin + n_net)
+    double l2_alpha = 0.0;
+};
+
+struct GoalProg {
+    int n = 0, E = 0;
+    std::vector<GoalRec> recs;
+    std::vector<int32_t> ngoal_ptr, egoal_ptr;
+    int net_begin = 0, n_net = 0;
+    double l2_alpha = 0.0;
+    mutable std::mutex mu;
+    mutable std::map<int, GoalProgDev> dev;
+    mutable std::map<int, void*> dev_block;
+};
+
+void set_error(const std::string& msg);
+int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fixed, Plan& plan);
+
+// shared-memory footprint of the fused direct kernel for half-bandwidth w
+inline int64_t direct_smem_bytes(int nf, int w) {
+    int64_t ld = (int64_t)nf | 1;                      // odd leading dimension: conflict-free diagonals
+    return 8 * ((int64_t)(w + 1) * ld + 3 * (int64_t)nf + 2 * (int64_t)(w + 1) + 16);
+}
+constexpr int64_t kDirectSmemLimit = 200 * 1024;
+
+}  // namespace dfdm
+
+struct dfdm_plan : dfdm::Plan {};
+struct dfdm_goalprog : dfdm::GoalProg {};

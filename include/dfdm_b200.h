@@ -1,0 +1,201 @@
+/*
+ * dfdm_b200 — C ABI of the B200-native force-density hot path.
+ *
+ * The reference (arpastrana/dfdm) is pure Python and has no FFI of its own; its boundary for this
+ * path is the Python API of src/dfdm/equilibrium/model.py, src/dfdm/losses/losses.py and
+ * src/dfdm/optimization.py.  Every entry point below names the reference interface it replaces
+ * (paths relative to /root/reference).  The binding a maintainer would add on the reference side is
+ * the ctypes stub shown in INTEGRATION.md (dfdm_b200/_lib.py is that stub, in use).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures (streams travel as void*,
+ *     i.e. a cudaStream_t; NULL = the legacy default stream)
+ *   - device entry points take DEVICE pointers, run asynchronously on `stream`, never allocate after
+ *     the workspace query, and leave per-design numerical verdicts in `status[B]`
+ *   - *_host entry points take HOST pointers and include the host<->device copies
+ *   - all floating point data is IEEE double; batches are design-major: q[B][E], xyz[B][n][3], ...
+ *   - return value: 0 on success, a negative DFDM_E* code otherwise; dfdm_last_error() explains it
+ *   - thread safety: a plan / goal program is immutable after creation and may be shared by any
+ *     number of threads, streams and devices; concurrent calls must use distinct workspaces
+ */
+#ifndef DFDM_B200_H
+#define DFDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFDM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DFDM_API __attribute__((visibility("default")))
+#else
+#define DFDM_API
+#endif
+
+/* error codes */
+#define DFDM_OK 0
+#define DFDM_EINVAL (-1)     /* bad argument (NULL, negative size, index out of range) */
+#define DFDM_ECUDA (-2)      /* CUDA runtime error; see dfdm_last_error() */
+#define DFDM_ENOMEM (-3)     /* workspace too small / allocation failed */
+#define DFDM_EUNSUPPORTED (-4)
+
+/* per-design status written by the solvers (numpy.linalg.LinAlgError territory in model.py:55) */
+#define DFDM_STATUS_OK 0
+#define DFDM_STATUS_SINGULAR 1        /* zero / non-finite pivot in the direct factorisation */
+#define DFDM_STATUS_NOT_CONVERGED 2   /* PCG hit maxiter (indefinite or ill-conditioned K) */
+#define DFDM_STATUS_NONFINITE 3       /* NaN / Inf in the result */
+
+/* solver selection */
+#define DFDM_SOLVER_AUTO 0
+#define DFDM_SOLVER_DIRECT 1   /* banded LDL^T in shared memory, one CTA per design, whole eval fused */
+#define DFDM_SOLVER_PCG 2      /* Jacobi-preconditioned CG on batch-interleaved CSR */
+
+typedef struct dfdm_plan dfdm_plan;
+typedef struct dfdm_goalprog dfdm_goalprog;
+
+typedef struct dfdm_options {
+    int32_t solver;          /* DFDM_SOLVER_*; AUTO picks DIRECT when the band fits shared memory */
+    int32_t pcg_maxiter;     /* <= 0: default 20 * sqrt(n_free) + 2000 */
+    double pcg_rtol;         /* <= 0: default 1e-12 on ||r|| / ||b|| per design and coordinate */
+    int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 */
+    int32_t reserved;
+} dfdm_options;
+
+typedef struct dfdm_plan_info {
+    int32_t n, n_edges, n_free, n_fixed;
+    int32_t nnz;                 /* stored entries of K = C_f^T Q C_f (full symmetric CSR, sorted columns) */
+    int32_t bandwidth_natural;   /* half-bandwidth of K in ascending free-node order */
+    int32_t bandwidth_solver;    /* half-bandwidth in the ordering the direct solver uses (RCM or natural) */
+    int32_t direct_fits;         /* 1 if the banded factor + 3 right-hand sides fit one CTA's shared memory */
+    int64_t direct_smem_bytes;
+    int32_t auto_solver;         /* what DFDM_SOLVER_AUTO resolves to */
+    int32_t reserved;
+} dfdm_plan_info;
+
+/* index arrays exposed for bit-exact parity tests (host pointers owned by the plan) */
+#define DFDM_ARR_FREE 0          /* int32[n_free]   structure.py:74-81  free_nodes  */
+#define DFDM_ARR_FIXED 1         /* int32[n_fixed]  structure.py:83-90  fixed_nodes */
+#define DFDM_ARR_FREEFIXED 2     /* int32[n]        structure.py:92-106 freefixed_nodes */
+#define DFDM_ARR_ROWPTR 3        /* int32[n_free+1] CSR of K in free order */
+#define DFDM_ARR_COLIDX 4        /* int32[nnz] */
+#define DFDM_ARR_EDGE_SLOTS 5    /* int32[E][4]: CSR slots (uu, vv, uv, vu) an edge scatters into, -1 if the endpoint is fixed */
+#define DFDM_ARR_SOLVER_PERM 6   /* int32[n_free]: free index at each position of the direct solver's ordering */
+#define DFDM_ARR_NODE_INC_PTR 7  /* int32[n+1]  node -> incident edges */
+#define DFDM_ARR_NODE_INC_EDGE 8 /* int32[2E] */
+#define DFDM_ARR_NODE_INC_SIGN 9 /* int32[2E]: C[e, node] = -1 (tail u) or +1 (head v); model.py:23,34 */
+
+DFDM_API const char* dfdm_last_error(void);
+DFDM_API int32_t dfdm_abi_version(void);
+
+/*
+ * Topology compiler.  Replaces EquilibriumStructure (src/dfdm/equilibrium/structure.py:11-106):
+ * node_index / edge_index are the caller's row numbering; connectivity (structure.py:63-72) is kept
+ * as the edge list itself (C[e,u] = -1, C[e,v] = +1); free_nodes / fixed_nodes / freefixed_nodes are
+ * DFDM_ARR_FREE / FIXED / FREEFIXED.  Also builds, once, what model.py:36-55 rebuilds on every call:
+ * the sparsity pattern of K and the scatter maps into it.
+ */
+DFDM_API int dfdm_plan_create(int32_t n, int32_t n_edges, const int32_t* edges /* [E][2] (u, v) */,
+                     const uint8_t* is_fixed /* [n] */, dfdm_plan** plan);
+DFDM_API void dfdm_plan_destroy(dfdm_plan* plan);
+DFDM_API int dfdm_plan_get_info(const dfdm_plan* plan, dfdm_plan_info* info);
+DFDM_API const int32_t* dfdm_plan_array(const dfdm_plan* plan, int32_t which, int64_t* length);
+
+/*
+ * Goal / loss program.  Replaces the object graph Loss -> LossTerm -> [Goal]
+ * (src/dfdm/losses/losses.py:10-87, src/dfdm/goals/goal.py:23-33, goals/helpers.py:19-37) by a flat
+ * table evaluated on the device.  Goal kinds: one per reference goal class.
+ */
+#define DFDM_GOAL_NODE_POINT 0               /* goals/nodegoal/pointgoal.py:11-28     params: target xyz */
+#define DFDM_GOAL_NODE_LINE 1                /* pointgoal.py:31-44                    params: a xyz, b xyz */
+#define DFDM_GOAL_NODE_PLANE 2               /* pointgoal.py:47-61                    params: origin xyz, normal xyz */
+#define DFDM_GOAL_NODE_RESIDUAL_FORCE 3      /* goals/nodegoal/residualgoal.py:12-25  params: target */
+#define DFDM_GOAL_NODE_RESIDUAL_VECTOR 4     /* residualgoal.py:28-39                 params: target xyz */
+#define DFDM_GOAL_NODE_RESIDUAL_DIRECTION 5  /* residualgoal.py:42-70                 params: target xyz (normalised on device) */
+#define DFDM_GOAL_EDGE_LENGTH 6              /* goals/edgegoal/lengthgoal.py:7-19     params: target */
+#define DFDM_GOAL_EDGE_FORCE 7               /* goals/edgegoal/forcegoal.py:7-19      params: target */
+#define DFDM_GOAL_EDGE_LOAD_PATH 8           /* goals/edgegoal/loadpathgoal.py:7-22   params: target */
+#define DFDM_GOAL_EDGE_VECTOR_ANGLE 9        /* goals/edgegoal/anglegoal.py:7-32      params: target (degrees), vector xyz */
+#define DFDM_GOAL_EDGE_DIRECTION 10          /* goals/edgegoal/directiongoal.py:7-25  params: target xyz */
+#define DFDM_GOAL_NETWORK_LOAD_PATH 11       /* goals/networkgoal/loadpathgoal.py:7-23 params: target */
+#define DFDM_N_GOAL_KINDS 12
+#define DFDM_GOAL_NPARAMS 6
+
+#define DFDM_TERM_SQUARED_ERROR 0        /* losses.py:38-45  alpha * sum(w (p - t)^2)  */
+#define DFDM_TERM_MEAN_SQUARED_ERROR 1   /* losses.py:48-55  alpha * mean(w (p - t)^2) over all entries of the term */
+#define DFDM_TERM_PREDICTION_ERROR 2     /* losses.py:58-64  alpha * sum(p) */
+
+DFDM_API int dfdm_goalprog_create(const dfdm_plan* plan, int32_t n_goals,
+                         const int32_t* kind /* [G] DFDM_GOAL_* */,
+                         const int32_t* element /* [G] node or edge row index; ignored for network goals */,
+                         const int32_t* term /* [G] index into the term arrays */,
+                         const double* weight /* [G] */,
+                         const double* params /* [G][DFDM_GOAL_NPARAMS] */,
+                         int32_t n_terms, const int32_t* term_kind /* [T] DFDM_TERM_* */,
+                         const double* term_alpha /* [T] */,
+                         double l2_alpha /* sum of L2Regularizer alphas, regularizers.py:19-20 */,
+                         dfdm_goalprog** prog);
+DFDM_API void dfdm_goalprog_destroy(dfdm_goalprog* prog);
+
+/* bytes of device scratch an evaluation of B designs needs (state outputs the caller does not ask for live here) */
+DFDM_API int64_t dfdm_workspace_bytes(const dfdm_plan* plan, int32_t batch, const dfdm_options* options);
+
+/*
+ * EquilibriumModel.__call__ (src/dfdm/equilibrium/model.py:63-79) for B designs.
+ * Outputs (any may be NULL): the EquilibriumState fields of state.py:11-18.
+ */
+DFDM_API int dfdm_forward(const dfdm_plan* plan, int32_t batch,
+                 const double* q /* [B][E] */, const double* loads /* [n][3] model.py:18 */,
+                 const double* xyz_fixed /* [n_fixed][3] model.py:19 */,
+                 double* xyz /* [B][n][3] */, double* residuals /* [B][n][3] */, double* vectors /* [B][E][3] */,
+                 double* lengths /* [B][E] */, double* forces /* [B][E] */, int32_t* status /* [B] */,
+                 void* workspace, int64_t workspace_bytes, const dfdm_options* options, void* stream);
+
+/*
+ * Loss.__call__ (losses.py:76-81) and grad(loss) (src/dfdm/optimization.py:61) in one pass:
+ * forward, goal / loss evaluation, closed-form adjoint with one extra solve on the same operator.
+ * dq may be NULL (value only).  State outputs as in dfdm_forward (any may be NULL).
+ */
+DFDM_API int dfdm_loss_and_grad(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t batch,
+                       const double* q, const double* loads, const double* xyz_fixed,
+                       double* loss /* [B] */, double* dq /* [B][E] */,
+                       double* xyz, double* residuals, double* vectors, double* lengths, double* forces,
+                       int32_t* status, void* workspace, int64_t workspace_bytes,
+                       const dfdm_options* options, void* stream);
+
+/*
+ * Generic reverse mode (what autograd's tape computes for an arbitrary scalar of the state):
+ * q_bar for given cotangents of (xyz, residuals, vectors, lengths, forces); any cotangent may be NULL.
+ * Used for constraint Jacobians (optimization.py:115-130) and torch.autograd interop.
+ */
+DFDM_API int dfdm_vjp(const dfdm_plan* plan, int32_t batch,
+             const double* q, const double* loads, const double* xyz_fixed,
+             const double* xyz_bar /* [B][n][3] */, const double* residuals_bar /* [B][n][3] */,
+             const double* vectors_bar /* [B][E][3] */, const double* lengths_bar /* [B][E] */,
+             const double* forces_bar /* [B][E] */,
+             double* dq /* [B][E] */, int32_t* status, void* workspace, int64_t workspace_bytes,
+             const dfdm_options* options, void* stream);
+
+/*
+ * Host-buffer variants: copy inputs to the current device, evaluate, copy results back, synchronise.
+ * Device memory is cached inside the library per (plan, device) and grown on demand.
+ */
+DFDM_API int dfdm_forward_host(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
+                      double* xyz, double* residuals, double* vectors, double* lengths, double* forces,
+                      int32_t* status, const dfdm_options* options);
+DFDM_API int dfdm_loss_and_grad_host(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t batch,
+                            const double* q, const double* loads, const double* xyz_fixed,
+                            double* loss, double* dq, int32_t* status, const dfdm_options* options);
+
+/* kernels launched by this library since load (all threads); bench.py reports the delta as gpu_launches */
+DFDM_API int64_t dfdm_launch_count(void);
+/* PCG iterations used by the most recent evaluation on this thread (forward solve, adjoint solve) */
+DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFDM_B200_H */

@@ -177,3 +177,28 @@ def case_arrays(case):
 def oracle_terms(case):
     """Term specs in the oracle's form ``(kind, goals, alpha)``."""
     return [(kind, goals, alpha) for kind, goals, alpha in case["terms"]]
+
+
+def program_inputs(case):
+    """Case term specs -> (goal rows, term rows, l2_alpha) for dfdm_b200.engine.GoalProgram."""
+    goals, terms, l2 = [], [], 0.0
+    for kind, specs, alpha in case["terms"]:
+        if kind == "L2Regularizer":
+            l2 += alpha
+            continue
+        t = len(terms)
+        terms.append((kind, alpha))
+        for spec in specs:
+            gkind, index, target, weight = spec[:4]
+            if gkind in ("NodeLine", "NodePlane"):
+                params = list(target[0]) + list(target[1])
+            elif gkind == "EdgeVectorAngle":
+                params = [target] + list(spec[4])
+            elif gkind == "NetworkLoadPath":
+                params = [0.0 if target is None else target]
+            elif np.ndim(target) == 0:
+                params = [target]
+            else:
+                params = list(target)
+            goals.append((gkind, index, t, weight, params))
+    return goals, terms, l2
