@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""
+bench.py — equilibrium+VJP evaluations per second on synthetic networks of the named shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid256|pillow|pringle|monkey_saddle|dome|arch]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference algorithm on the host cores (oracle port)
+
+One "step" = one pass of the hot path over one batch: for every design of the batch, equilibrium
+state + scalar loss + full dL/dq.  Default workload: BASELINE.json configs[4] (256x256 free-node quad
+cable net, batch 256 per GPU, PCG path) — the largest single-GPU configuration and the one whose
+kernels the HBM roofline applies to.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "equilibrium+VJP evals/sec"
+UNIT = "evals/s"
+DEFAULT_BATCH = {"grid256": 256, "pillow": 1024, "pringle": 1024, "monkey_saddle": 4096, "dome": 512, "arch": 64}
+L2_BYTES = 126 * 1024 * 1024
+
+
+# --------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------
+
+def make_workload(name, batch):
+    from dfdm_b200 import workloads as W
+    import cases
+    if name.startswith("grid"):
+        nfree = int(name[4:])
+        edges, fixed, xyz, loads, q0 = W.grid_arrays(nfree)
+        q = W.sample_q(q0, batch, seed=6, spread=0.2, relative=True)
+        lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+        goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+        return {"name": name, "edges": edges, "is_fixed": fixed, "xyz": xyz, "loads": loads, "q": q,
+                "program": (goals, [("SquaredError", 1.0)], 0.1), "sparse": {"targets": lengths0, "weight": 1.0, "l2": 0.1},
+                "loss": "SquaredError(EdgeLengthGoal for every edge, target = initial length) + L2Regularizer(0.1)"}
+    builders = {"pillow": (cases.case_pillow, 2, 0.1, False, None, None),
+                "pringle": (cases.case_pringle, 3, 0.1, False, -5.0, -0.1),
+                "monkey_saddle": (cases.case_monkey_saddle, 4, 1.0, True, -20.0, -0.01),
+                "dome": (cases.case_dome, 5, 0.2, True, None, None),
+                "arch": (lambda: _arch_case(), 1, 0.1, False, None, None)}
+    build, seed, spread, relative, lo, hi = builders[name]
+    case = build()
+    edges, fixed, xyz, loads = cases.case_arrays(case)
+    q0 = np.asarray(case["network"].edges_forcedensities(), dtype=np.float64)
+    q = W.sample_q(q0, batch, seed=seed, spread=spread, relative=relative, lo=lo, hi=hi)
+    return {"name": name, "edges": edges, "is_fixed": fixed, "xyz": xyz, "loads": loads, "q": q,
+            "program": cases.program_inputs(case), "terms": cases.oracle_terms(case), "sparse": None,
+            "loss": "+".join(t[0] for t in case["terms"])}
+
+
+def _arch_case():
+    from dfdm_b200 import workloads as W
+    net = W.arch(5000)
+    goals = [("NodeResidualDirection", 0, [-1.0, 0.0, -0.4], 1.0), ("NodeResidualDirection", 5000, [1.0, 0.0, -0.4], 1.0)]
+    return {"name": "arch", "network": net, "q": None, "terms": [("SquaredError", goals, 1.0)]}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated (oracle), all host cores, bounded sample
+# --------------------------------------------------------------------------------------
+
+_CPU = {}
+
+
+def _cpu_init(wl):
+    from oracle import fdm_oracle as O
+    import torch
+    torch.set_num_threads(1)
+    fixed_rows = np.nonzero(wl["is_fixed"])[0]
+    if wl["sparse"]:
+        _CPU["model"] = O.SparseModel(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"], wl["loads"], wl["xyz"][fixed_rows])
+    else:
+        s = O.Structure(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
+        _CPU["model"] = O.Model(s, wl["loads"], wl["xyz"][fixed_rows])
+    _CPU["wl"] = wl
+
+
+def _cpu_eval(q):
+    from oracle import fdm_oracle as O
+    wl, model = _CPU["wl"], _CPU["model"]
+    if wl["sparse"]:
+        sp = wl["sparse"]
+        loss, dq, _ = model.loss_and_grad_edge_length(q, sp["targets"], sp["weight"], sp["l2"])
+    else:
+        loss, dq = O.loss_and_grad(wl["terms"], q, model)
+    return float(loss)
+
+
+def cpu_arm(wl, budget_s=20.0, steps=1):
+    """Returns (evals/s, cores, sample description, ms per step).  Each step evaluates `sample` designs on all cores."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    _cpu_init(wl)
+    t0 = time.perf_counter()
+    _cpu_eval(wl["q"][0])
+    one = time.perf_counter() - t0
+    sample = int(max(cores, min(len(wl["q"]), cores * max(1.0, budget_s / max(one, 1e-6)) / max(steps, 1))))
+    sample = max(cores, (sample // cores) * cores)
+    sample = min(sample, max(cores, (len(wl["q"]) // cores) * cores)) if len(wl["q"]) >= cores else len(wl["q"])
+    qs = [wl["q"][k % len(wl["q"])] for k in range(sample)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(wl,)) as pool:
+        pool.map(_cpu_eval, qs[:cores])                      # warm-up: imports, first factorisation
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_eval, qs, chunksize=max(1, sample // cores))
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    kind = "sparse CPU restatement (scipy CSR + SuperLU + hand adjoint; dense reference path infeasible at this size)" \
+        if wl["sparse"] else "oracle port of the reference (dense NumPy forward + torch-f64 tape gradient)"
+    desc = "%d designs of workload %s per step, %d processes x 1 thread, %s" % (sample, wl["name"], cores, kind)
+    return sample * steps / total, cores, desc, 1e3 * total / steps
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(kernel, workload):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fp:
+            return json.load(fp).get(workload, {}).get(kernel)
+    return None
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dfdm_b200 import _lib
+    from dfdm_b200.engine import Plan, GoalProgram, Evaluator
+    from dfdm_b200.distributed import gather_designs
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    batch = args.batch or DEFAULT_BATCH.get(args.workload, 256)
+    wl = make_workload(args.workload, batch * world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, desc, _ = cpu_arm(wl, budget_s=args.cpu_budget)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    q_all = wl["q"]
+    lo, hi = rank * batch, (rank + 1) * batch                      # weak scaling: fixed work per GPU
+    q_host = torch.from_numpy(np.ascontiguousarray(q_all[lo:hi])).pin_memory()
+    plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
+    fixed_rows = np.nonzero(wl["is_fixed"])[0]
+    ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every)
+    prog = GoalProgram(plan, *wl["program"])
+    q_dev = q_host.to(device)
+    E = plan.n_edges
+    solver = plan.auto_solver if args.solver == "auto" else args.solver
+
+    def step():
+        out = ev.loss_and_grad(prog, q_dev)
+        if world > 1:                                               # the one collective of a batched evaluation
+            loss_all = gather_designs(out["loss"], batch * world)
+            dq_all = gather_designs(out["dq"], batch * world)
+            return out, loss_all, dq_all
+        return out, out["loss"], out["dq"]
+
+    working_set = _lib.lib.dfdm_workspace_bytes(plan.handle, batch, None) if solver == "pcg" else batch * E * 8 * 12
+    flush = working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(2 * L2_BYTES // 8, dtype=torch.float64, device=device) if flush else None
+
+    for _ in range(args.warmup):
+        out, _, _ = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    status = out["status"].cpu().numpy()
+    iters = _lib.last_pcg_iterations() if solver == "pcg" else (0, 0)
+
+    # ---- timed region: device-resident inputs --------------------------------------------------------
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for k in range(args.steps):
+        if flush:
+            flush_buf.fill_(float(k))
+        starts[k].record()
+        step()
+        ends[k].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    prof_ms, prof_count = _lib.profile_read()
+    _lib.profile_enable(False)
+    ms_total = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=device)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(tmax[0]), int(t[1])
+    value = batch * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host buffers through the C ABI, copies inside the timed region --------------------
+    loss_h = torch.empty(batch, dtype=torch.float64).pin_memory().numpy()
+    dq_h = torch.empty(batch, E, dtype=torch.float64).pin_memory().numpy()
+    status_h = torch.empty(batch, dtype=torch.int32).pin_memory().numpy()
+    q_np = q_host.numpy()
+    ev.loss_and_grad_host(prog, q_np, loss_h, dq_h, status_h)     # warm the cached arena
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.loss_and_grad_host(prog, q_np, loss_h, dq_h, status_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+    h2d = q_np.nbytes + ev.loads_host.nbytes + ev.xyz_fixed_host.nbytes
+    d2h = loss_h.nbytes + dq_h.nbytes + status_h.nbytes
+    same = bool(np.allclose(loss_h, out["loss"].cpu().numpy(), rtol=1e-12, atol=0))
+
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    nf, nnz = plan.n_free, plan.nnz
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
+                       "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
+                       "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
+                       "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients)" % world,
+                       "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
+                       "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
+            "clocks": clocks,
+            "e2e": {"value": batch * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": int(d2h) * world, "api": "dfdm_loss_and_grad_host (pinned host buffers)"},
+            "gpu_launches": launches}
+    if solver == "pcg" and sum(prof_count) > 0:
+        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": 80.0 * nf * batch}
+        kernels = []
+        for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction")):
+            if prof_count[k]:
+                avg_ms = prof_ms[k] / prof_count[k]
+                kernels.append({"kernel": name, "launches": prof_count[k], "avg_ms": avg_ms, "share_of_step": prof_ms[k] / ms_total,
+                                "algorithmic_bytes": alg[name], "achieved_gbs": alg[name] / (avg_ms * 1e-3) / 1e9})
+        top = max(kernels, key=lambda kk: kk["share_of_step"])
+        line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": top["achieved_gbs"] / peak, "traffic": traffic_for(top["kernel"], wl["name"]),
+                            "peak_source": peak_src, "timing": "CUDA events on the launch stream after every PCG launch, timed region"}
+        line["kernels"] = kernels
+    else:
+        # direct path: one fused kernel per step; mandatory I/O only (q in, loss + dq out)
+        alg = batch * (16.0 * E + 8.0)
+        ms = ms_total / args.steps
+        line["roofline"] = {"bound": "hbm", "kernel": "k_direct_eval", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic_for("k_direct_eval", wl["name"]),
+                            "peak_source": peak_src,
+                            "note": "shared-memory factorisation: latency / FP64-issue bound, not HBM bound; fraction reported for completeness"}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    return line
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return None
+    batch = args.batch or DEFAULT_BATCH.get(args.workload, 256)
+    wl = make_workload(args.workload, batch)
+    v, cores, desc, ms = cpu_arm(wl, budget_s=args.cpu_budget, steps=max(1, args.steps))
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "loss": wl["loss"],
+                       "note": "CPU arm: rank 0 only, host cores; the reference has no GPU or multi-process path"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="grid256")
+    ap.add_argument("--batch", type=int, default=0, help="designs per GPU (default: the configuration's own)")
+    ap.add_argument("--solver", default="auto", choices=["auto", "direct", "pcg"])
+    ap.add_argument("--pcg-rtol", type=float, default=0.0)
+    ap.add_argument("--pcg-check-every", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = reference_arm(args, rank, world)
+    else:
+        if world != args.gpus and rank == 0:
+            print("note: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+        line = gpu_arm(args, rank, world, local_rank)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

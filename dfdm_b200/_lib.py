@@ -32,7 +32,7 @@ TERM_KINDS = {"SquaredError": 0, "MeanSquaredError": 1, "PredictionError": 2}
 SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan_destroy", "dfdm_plan_get_info",
            "dfdm_plan_array", "dfdm_goalprog_create", "dfdm_goalprog_destroy", "dfdm_workspace_bytes", "dfdm_forward",
            "dfdm_loss_and_grad", "dfdm_vjp", "dfdm_forward_host", "dfdm_loss_and_grad_host", "dfdm_launch_count",
-           "dfdm_last_pcg_iterations"]
+           "dfdm_last_pcg_iterations", "dfdm_profile_enable", "dfdm_profile_read"]
 
 
 class Options(C.Structure):
@@ -78,6 +78,10 @@ def _load():
     lib.dfdm_launch_count.restype = i64
     lib.dfdm_last_pcg_iterations.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     lib.dfdm_last_pcg_iterations.restype = None
+    lib.dfdm_profile_enable.argtypes = [i32]
+    lib.dfdm_profile_enable.restype = None
+    lib.dfdm_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]
+    lib.dfdm_profile_read.restype = None
     for name in SYMBOLS:
         getattr(lib, name)
     if lib.dfdm_abi_version() != 1:
@@ -117,3 +121,14 @@ def last_pcg_iterations():
     f, a = C.c_int32(0), C.c_int32(0)
     lib.dfdm_last_pcg_iterations(C.byref(f), C.byref(a))
     return f.value, a.value
+
+
+def profile_enable(on=True):
+    lib.dfdm_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    ms = (C.c_double * 4)()
+    count = (C.c_int64 * 4)()
+    lib.dfdm_profile_read(ms, count)
+    return list(ms), list(count)

@@ -8,6 +8,8 @@ namespace dfdm {
 
 std::atomic<long long> g_launches{0};
 void last_pcg_iterations(int* fwd, int* adj);
+void profile_enable(int on);
+void profile_read(double* ms, long long* count);
 
 // ---- device mirrors ------------------------------------------------------------------------------
 
@@ -400,6 +402,18 @@ void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters) {
     last_pcg_iterations(&f, &a);
     if (forward_iters) *forward_iters = f;
     if (adjoint_iters) *adjoint_iters = a;
+}
+
+void dfdm_profile_enable(int32_t on) { profile_enable(on); }
+
+void dfdm_profile_read(double* ms, int64_t* count) {
+    double m[4];
+    long long c[4];
+    profile_read(m, c);
+    for (int k = 0; k < 4; ++k) {
+        if (ms) ms[k] = m[k];
+        if (count) count[k] = (int64_t)c[k];
+    }
 }
 
 }  // extern "C"

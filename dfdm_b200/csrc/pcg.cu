@@ -14,6 +14,8 @@
 // Reference being replaced: np.linalg.solve in src/dfdm/equilibrium/model.py:55 (for networks whose
 // banded factor does not fit shared memory) plus the assembly of model.py:50-54 and the
 // post-processing of model.py:21-34, batched.
+#include <vector>
+
 #include "common.cuh"
 
 namespace dfdm {
@@ -628,6 +630,46 @@ int64_t pcg_workspace(const Plan& P, int B) {
     return bump.off;
 }
 
+// Optional per-kernel timing of the PCG loop (bench.py's roofline leg): one event after every launch,
+// resolved at the convergence polls, so the measured interval of a kernel includes its launch gap.
+struct Profile {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> kind;
+    double ms[4] = {0, 0, 0, 0};
+    long long count[4] = {0, 0, 0, 0};
+};
+static Profile g_prof;
+
+void profile_enable(int on) {
+    g_prof.on = on != 0;
+    for (int k = 0; k < 4; ++k) { g_prof.ms[k] = 0.0; g_prof.count[k] = 0; }
+}
+void profile_read(double* ms, long long* count) {
+    for (int k = 0; k < 4; ++k) { ms[k] = g_prof.ms[k]; count[k] = g_prof.count[k]; }
+}
+static void prof_mark(cudaStream_t st, int kind, size_t& used) {
+    if (!g_prof.on) return;
+    if (used >= g_prof.ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g_prof.ev.push_back(e);
+        g_prof.kind.push_back(0);
+    }
+    g_prof.kind[used] = kind;
+    cudaEventRecord(g_prof.ev[used++], st);
+}
+static void prof_resolve(size_t used) {
+    if (!g_prof.on) return;
+    for (size_t k = 1; k < used; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[k - 1], g_prof.ev[k]) == cudaSuccess && g_prof.kind[k] >= 0) {
+            g_prof.ms[g_prof.kind[k]] += ms;
+            g_prof.count[g_prof.kind[k]] += 1;
+        }
+    }
+}
+
 static int pcg_solve(const PlanDev& P, const LaneCfg& cfg, int B, PcgBuffers& w, const dfdm_options& opt, cudaStream_t st,
                      int32_t* host_flag, int* iters_out) {
     int grid = cfg.nchunks * cfg.nslabs;
@@ -641,16 +683,22 @@ static int pcg_solve(const PlanDev& P, const LaneCfg& cfg, int B, PcgBuffers& w,
     int it = 0;
     while (it < maxiter) {
         int stop = std::min(maxiter, it + every);
+        size_t used = 0;
+        prof_mark(st, -1, used);
         for (; it < stop; ++it) {
             k_pcg_spmv<<<grid, kThreads, 0, st>>>(P, cfg, B, w.vals, w.p, w.Ap, w.S);
             DFDM_LAUNCH_OK("k_pcg_spmv");
+            prof_mark(st, 0, used);
             k_pcg_update<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S, rtol * rtol);
             DFDM_LAUNCH_OK("k_pcg_update");
+            prof_mark(st, 1, used);
             k_pcg_direction<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.p, w.S);
             DFDM_LAUNCH_OK("k_pcg_direction");
+            prof_mark(st, 2, used);
         }
         DFDM_CUDA_OK(cudaMemcpyAsync(host_flag, w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         DFDM_CUDA_OK(cudaStreamSynchronize(st));
+        prof_resolve(used);
         if (*host_flag == 0) break;
     }
     *iters_out = it;

@@ -195,6 +195,17 @@ DFDM_API int64_t dfdm_launch_count(void);
 /* PCG iterations used by the most recent evaluation on this thread (forward solve, adjoint solve) */
 DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters);
 
+/*
+ * Per-kernel timing of the PCG loop for roofline accounting: when enabled, a CUDA event is recorded on
+ * the launch stream after every PCG kernel and resolved at the convergence polls.
+ * ms / count are indexed by DFDM_PROF_* (4 entries each).  Not thread safe; meant for bench.py.
+ */
+#define DFDM_PROF_SPMV 0       /* k_pcg_spmv:      Ap = K p, p.Ap            algorithmic bytes 8 nnz + 48 n_free per design */
+#define DFDM_PROF_UPDATE 1     /* k_pcg_update:    x, r update, r.z, r.r     152 n_free per design */
+#define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: p = z + beta p            80 n_free per design */
+DFDM_API void dfdm_profile_enable(int32_t on);
+DFDM_API void dfdm_profile_read(double* ms /* [4] */, int64_t* count /* [4] */);
+
 #ifdef __cplusplus
 }
 #endif
