@@ -104,15 +104,16 @@ def cpu_arm(wl, budget_s=20.0, steps=1):
     """Returns (evals/s, cores, sample description, ms per step).  Each step evaluates `sample` designs on all cores."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    _cpu_init(wl)
-    t0 = time.perf_counter()
-    _cpu_eval(wl["q"][0])
-    one = time.perf_counter() - t0
+    ctx = mp.get_context("spawn")          # workers must not inherit a parent that already ran autograd / CUDA
+    with ctx.Pool(1, initializer=_cpu_init, initargs=(wl,)) as probe:
+        probe.map(_cpu_eval, [wl["q"][0]])
+        t0 = time.perf_counter()
+        probe.map(_cpu_eval, [wl["q"][0]])
+        one = time.perf_counter() - t0
     sample = int(max(cores, min(len(wl["q"]), cores * max(1.0, budget_s / max(one, 1e-6)) / max(steps, 1))))
     sample = max(cores, (sample // cores) * cores)
     sample = min(sample, max(cores, (len(wl["q"]) // cores) * cores)) if len(wl["q"]) >= cores else len(wl["q"])
     qs = [wl["q"][k % len(wl["q"])] for k in range(sample)]
-    ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(wl,)) as pool:
         pool.map(_cpu_eval, qs[:cores])                      # warm-up: imports, first factorisation
         times = []
@@ -220,7 +221,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every)
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter)
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -368,6 +369,7 @@ def main():
     ap.add_argument("--solver", default="auto", choices=["auto", "direct", "pcg"])
     ap.add_argument("--pcg-rtol", type=float, default=0.0)
     ap.add_argument("--pcg-check-every", type=int, default=0)
+    ap.add_argument("--pcg-maxiter", type=int, default=0, help="cap PCG iterations (kernel tuning runs only: results not converged)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

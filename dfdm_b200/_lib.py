@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdfdm_b200.so")
+LIB_PATH = os.environ.get("DFDM_B200_LIB") or os.path.join(HERE, "libdfdm_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 STATUS_OK, STATUS_SINGULAR, STATUS_NOT_CONVERGED, STATUS_NONFINITE = 0, 1, 2, 3

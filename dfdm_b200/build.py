@@ -32,19 +32,24 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """``defines`` / ``out`` build a tuning variant of the library elsewhere (tools/ only); the product is LIB."""
+    target = out or LIB
+    if out is None and not force and not stale():
         return LIB
+    objdir = CSRC if out is None else os.path.dirname(os.path.abspath(out))
+    os.makedirs(objdir, exist_ok=True)
+    tag = "" if out is None else "." + os.path.splitext(os.path.basename(out))[0]
     objs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "cu", "-dc" if False else "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + tag + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+              ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [_nvcc()] + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [_nvcc()] + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", target] + objs
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

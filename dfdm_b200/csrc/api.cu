@@ -22,7 +22,7 @@ static int upload_plan(const Plan& P, int device, PlanDev& out) {
     }
     const std::vector<int32_t>* arrays[] = {&P.edges, &P.node_src, &P.free_nodes, &P.rowptr, &P.colidx, &P.diagslot,
                                             &P.finc_ptr, &P.finc_edge, &P.finc_code, &P.ninc_ptr, &P.ninc_edge, &P.ninc_sign,
-                                            &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code};
+                                            &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code, &P.ell_col, &P.ell_slot};
     constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
     int64_t offs[NA], total = 0;
     for (int k = 0; k < NA; ++k) {
@@ -40,6 +40,7 @@ static int upload_plan(const Plan& P, int device, PlanDev& out) {
     d.edges = at(0); d.node_src = at(1); d.free_nodes = at(2); d.rowptr = at(3); d.colidx = at(4); d.diagslot = at(5);
     d.finc_ptr = at(6); d.finc_edge = at(7); d.finc_code = at(8); d.ninc_ptr = at(9); d.ninc_edge = at(10); d.ninc_sign = at(11);
     d.perm = at(12); d.pos = at(13); d.sinc_ptr = at(14); d.sinc_edge = at(15); d.sinc_code = at(16);
+    d.ell_w = P.ell_w; d.ell_col = at(17); d.ell_slot = at(18);
     P.dev[device] = d;
     P.dev_block[device] = block;
     out = d;

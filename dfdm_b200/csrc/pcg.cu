@@ -166,119 +166,237 @@ __global__ void __launch_bounds__(kThreads) k_assemble(PlanDev P, LaneCfg cfg, i
 
 // ------------------------------------------------------------------------------------------------
 // PCG kernels.  Vectors x, r, p, Ap are [nf][3][B].
+//
+// One thread per (row, coordinate, design): CTAs of 384 threads = (rows x 3 coordinates) x lanes, so
+// a thread keeps ~5 loads in flight in ~32 registers and the SM stays fully occupied; the three
+// coordinate threads of a row share its matrix values through L1.  Column / slot indices come from
+// a padded (ELL) copy of the pattern so that they depend on the row number only - no rowptr -> colidx
+// -> data chain - and the next row's indices are fetched while the current row's data is in flight.
 // ------------------------------------------------------------------------------------------------
 
-// x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
-__global__ void __launch_bounds__(kThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                      const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
-                                                      PcgScalars S) {
-    LANE_SETUP();
-    double v[6] = {0, 0, 0, 0, 0, 0};
-    if (live) {
-        for (int f = row0; f < nf; f += rstride) {
-            double di = dinv[(size_t)f * B + b];
+constexpr int kVecThreads = 384;
+
+#define VEC_SETUP()                                                         \
+    const int cbl = 1 << cfg.shift;                                         \
+    const int chunk = blockIdx.x % cfg.nchunks;                             \
+    const int slab = blockIdx.x / cfg.nchunks;                              \
+    const int bl = threadIdx.x & (cbl - 1);                                 \
+    const int rl = threadIdx.x >> cfg.shift;                                \
+    const int c = rl % 3;                                                   \
+    const int rows_cta = (kVecThreads >> cfg.shift) / 3;                    \
+    const int b = chunk * cbl + bl;                                         \
+    const bool live = b < B;                                                \
+    const int row0 = slab * rows_cta + rl / 3;                              \
+    const int rstride = cfg.nslabs * rows_cta;                              \
+    (void)live; (void)row0; (void)rstride; (void)chunk; (void)slab; (void)bl; (void)c;
+
+// Reduce NV per-thread values (each belonging to the thread's coordinate c) over the rows of this CTA
+// and publish partial[slab][k*3 + c][b].  Returns true in the CTA that arrived last for its chunk.
+template <int NV>
+__device__ bool publish_vec(const double (&v)[NV], const LaneCfg& cfg, int B, double* partial, int32_t* tickets) {
+    __shared__ double red[NV][kVecThreads];
+    __shared__ int s_last;
+    VEC_SETUP();
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                size_t o = ((size_t)f * 3 + c) * B + b;
-                double rc = r[o];
-                double z = rc * di;
-                x[o] = 0.0;
-                p[o] = z;
-                v[c] += rc * z;
-                v[3 + c] += rc * rc;
-            }
+    for (int k = 0; k < NV; ++k) red[k][threadIdx.x] = v[k];
+    __syncthreads();
+    if (rl < 3 && live) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int r = 0; r < rows_cta; ++r) s += red[k][((r * 3 + c) << cfg.shift) + bl];
+            partial[((size_t)slab * (3 * NV) + k * 3 + c) * B + b] = s;
         }
     }
-    if (publish_partials<6>(v, cfg, B, S.partial, S.tickets)) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = atomicAdd(&tickets[chunk], 1);
+        s_last = (t == cfg.nslabs - 1);
+        if (s_last) tickets[chunk] = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
+__global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                         const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
+                                                         PcgScalars S) {
+    VEC_SETUP();
+    double v[2] = {0, 0};
+    if (live) {
+        for (int f = row0; f < nf; f += rstride) {
+            size_t o = ((size_t)f * 3 + c) * B + b;
+            double rc = r[o];
+            double z = rc * dinv[(size_t)f * B + b];
+            x[o] = 0.0;
+            p[o] = z;
+            v[0] += rc * z;
+            v[1] += rc * rc;
+        }
+    }
+    if (publish_vec<2>(v, cfg, B, S.partial, S.tickets)) {
         int fresh = 0;
         for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
-            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            int cc = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
             if (b2 >= B) continue;
-            double rho = sum_slabs<6>(S.partial, c, b2, B, cfg.nslabs);
-            double bb = sum_slabs<6>(S.partial, 3 + c, b2, B, cfg.nslabs);
-            S.rho[c * B + b2] = rho;
-            S.bb[c * B + b2] = bb;
-            S.beta[c * B + b2] = 0.0;
+            double rho = sum_slabs<6>(S.partial, cc, b2, B, cfg.nslabs);
+            double bb = sum_slabs<6>(S.partial, 3 + cc, b2, B, cfg.nslabs);
+            S.rho[cc * B + b2] = rho;
+            S.bb[cc * B + b2] = bb;
+            S.beta[cc * B + b2] = 0.0;
             int frozen = (bb == 0.0 || !(rho != 0.0)) ? 1 : 0;     // zero right-hand side: x = 0 is exact
-            S.frozen[c * B + b2] = frozen;
+            S.frozen[cc * B + b2] = frozen;
             fresh += frozen ? 0 : 1;
         }
         if (fresh) atomicAdd(S.n_active, fresh);
     }
 }
 
+#ifndef DFDM_SPMV_BATCH
+#define DFDM_SPMV_BATCH 5
+#endif
+#ifndef DFDM_SPMV_PREFETCH
+#define DFDM_SPMV_PREFETCH 0
+#endif
+#ifndef DFDM_SPMV_MINBLOCKS
+#define DFDM_SPMV_MINBLOCKS 4
+#endif
+#ifndef DFDM_UPD_MINBLOCKS
+#define DFDM_UPD_MINBLOCKS 3
+#endif
+constexpr int kSpmvBatch = DFDM_SPMV_BATCH;
+
 // Ap = K p ; sigma = p . Ap ; alpha = rho / sigma
-__global__ void __launch_bounds__(kThreads) k_pcg_spmv(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ vals,
-                                                      const double* __restrict__ p, double* __restrict__ Ap, PcgScalars S) {
+// One thread per (row, design) carrying the three coordinates, so a matrix value is loaded once and
+// used three times (a thread per coordinate triples the value requests and loses on L1/L2 traffic).
+// All loads of a batch of row entries are issued before their first use.
+__global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(PlanDev P, LaneCfg cfg, int B,
+                                                                          const double* __restrict__ vals,
+                                                                          const double* __restrict__ p, double* __restrict__ Ap,
+                                                                          PcgScalars S) {
     if (__ldcg(&S.n_active[1]) == 0) return;
     LANE_SETUP();
     double v[3] = {0, 0, 0};
     if (live) {
-        for (int f = row0; f < P.nf; f += rstride) {
-            int k0 = P.rowptr[f], k1 = P.rowptr[f + 1];
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            for (int k = k0; k < k1; ++k) {
-                double a = vals[(size_t)k * B + b];
-                size_t o = (size_t)P.colidx[k] * 3 * B + b;
-                a0 += a * p[o];
-                a1 += a * p[o + B];
-                a2 += a * p[o + 2 * (size_t)B];
+        const int W = P.ell_w;
+        const size_t sB = (size_t)B;
+        const double* pb = p + b;
+        const double* vb = vals + b;
+        int col[kSpmvBatch];
+        int f = row0, k0 = 0, k1 = 0;
+        if (f < P.nf) {
+            k0 = P.rowptr[f];
+            k1 = P.rowptr[f + 1];
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
+        }
+        while (f < P.nf) {
+            double a[kSpmvBatch], x0[kSpmvBatch], x1[kSpmvBatch], x2[kSpmvBatch];
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) {
+                a[u] = k0 + u < k1 ? vb[(size_t)(k0 + u) * sB] : 0.0;
+                const double* pj = pb + (size_t)col[u] * 3 * sB;
+                x0[u] = pj[0];
+                x1[u] = pj[sB];
+                x2[u] = pj[2 * sB];
             }
-            size_t o = (size_t)f * 3 * B + b;
-            Ap[o] = a0;
-            Ap[o + B] = a1;
-            Ap[o + 2 * (size_t)B] = a2;
-            v[0] += p[o] * a0;
-            v[1] += p[o + B] * a1;
-            v[2] += p[o + 2 * (size_t)B] * a2;
+            const size_t od = (size_t)f * 3 * sB + b;
+            const double d0 = p[od], d1 = p[od + sB], d2 = p[od + 2 * sB];
+            const int fn = f + rstride;
+#if DFDM_SPMV_PREFETCH
+            int ncol[kSpmvBatch], nk0 = 0, nk1 = 0;
+            if (fn < P.nf) {
+                nk0 = P.rowptr[fn];
+                nk1 = P.rowptr[fn + 1];
+#pragma unroll
+                for (int u = 0; u < kSpmvBatch; ++u) ncol[u] = u < W ? P.ell_col[(size_t)fn * W + u] : fn;
+            }
+#endif
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) {
+                a0 += a[u] * x0[u];
+                a1 += a[u] * x1[u];
+                a2 += a[u] * x2[u];
+            }
+            for (int k = k0 + kSpmvBatch; k < k1; ++k) {          // rows wider than one batch
+                double ak = vb[(size_t)k * sB];
+                const double* pj = pb + (size_t)P.colidx[k] * 3 * sB;
+                a0 += ak * pj[0];
+                a1 += ak * pj[sB];
+                a2 += ak * pj[2 * sB];
+            }
+            Ap[od] = a0;
+            Ap[od + sB] = a1;
+            Ap[od + 2 * sB] = a2;
+            v[0] += d0 * a0;
+            v[1] += d1 * a1;
+            v[2] += d2 * a2;
+            f = fn;
+#if DFDM_SPMV_PREFETCH
+            k0 = nk0;
+            k1 = nk1;
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) col[u] = ncol[u];
+#else
+            if (f < P.nf) {
+                k0 = P.rowptr[f];
+                k1 = P.rowptr[f + 1];
+#pragma unroll
+                for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
+            }
+#endif
         }
     }
     if (publish_partials<3>(v, cfg, B, S.partial, S.tickets)) {
         for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
-            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            int cc = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
             if (b2 >= B) continue;
-            double sigma = sum_slabs<3>(S.partial, c, b2, B, cfg.nslabs);
+            double sigma = sum_slabs<3>(S.partial, cc, b2, B, cfg.nslabs);
             double al = 0.0;
-            if (!S.frozen[c * B + b2] && sigma != 0.0) al = S.rho[c * B + b2] / sigma;
+            if (!S.frozen[cc * B + b2] && sigma != 0.0) al = S.rho[cc * B + b2] / sigma;
             if (!isfinite(al)) al = 0.0;
-            S.alpha[c * B + b2] = al;
+            S.alpha[cc * B + b2] = al;
         }
     }
 }
 
 // x += alpha p ; r -= alpha Ap ; rho' = r . (r/diag) ; rr = r.r ; beta = rho'/rho ; convergence
-__global__ void __launch_bounds__(kThreads) k_pcg_update(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                        const double* __restrict__ p, const double* __restrict__ Ap,
-                                                        double* __restrict__ x, double* __restrict__ r, PcgScalars S, double tol2) {
+__global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(int nf, LaneCfg cfg, int B,
+                                                                              const double* __restrict__ dinv,
+                                                                              const double* __restrict__ p,
+                                                                              const double* __restrict__ Ap, double* __restrict__ x,
+                                                                              double* __restrict__ r, PcgScalars S, double tol2) {
     // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
     if (__ldcg(&S.n_active[1]) == 0) return;
-    LANE_SETUP();
-    double v[6] = {0, 0, 0, 0, 0, 0};
+    VEC_SETUP();
+    double v[2] = {0, 0};
     if (live) {
-        double al[3] = {__ldcg(&S.alpha[b]), __ldcg(&S.alpha[B + b]), __ldcg(&S.alpha[2 * B + b])};
+        const double al = __ldcg(&S.alpha[c * B + b]);
+#pragma unroll 2
         for (int f = row0; f < nf; f += rstride) {
+            size_t o = ((size_t)f * 3 + c) * B + b;
             double di = dinv[(size_t)f * B + b];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                size_t o = ((size_t)f * 3 + c) * B + b;
-                double pc = p[o], ac = Ap[o];
-                x[o] += al[c] * pc;
-                double rc = r[o] - al[c] * ac;
-                r[o] = rc;
-                v[c] += rc * rc * di;
-                v[3 + c] += rc * rc;
-            }
+            double pc = p[o], ac = Ap[o], xc = x[o], rc = r[o];
+            x[o] = xc + al * pc;
+            rc -= al * ac;
+            r[o] = rc;
+            v[0] += rc * rc * di;
+            v[1] += rc * rc;
         }
     }
-    if (publish_partials<6>(v, cfg, B, S.partial, S.tickets)) {
+    if (publish_vec<2>(v, cfg, B, S.partial, S.tickets)) {
         int done = 0;
         for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
-            int c = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            int cc = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
             if (b2 >= B) continue;
-            int o = c * B + b2;
+            int o = cc * B + b2;
             if (S.frozen[o]) { S.beta[o] = 0.0; continue; }
-            double rho_new = sum_slabs<6>(S.partial, c, b2, B, cfg.nslabs);
-            double rr = sum_slabs<6>(S.partial, 3 + c, b2, B, cfg.nslabs);
+            double rho_new = sum_slabs<6>(S.partial, cc, b2, B, cfg.nslabs);
+            double rr = sum_slabs<6>(S.partial, 3 + cc, b2, B, cfg.nslabs);
             double rho_old = S.rho[o];
             double be = rho_old != 0.0 ? rho_new / rho_old : 0.0;
             if (!isfinite(be)) be = 0.0;
@@ -297,20 +415,17 @@ __global__ void __launch_bounds__(kThreads) k_pcg_update(int nf, LaneCfg cfg, in
 }
 
 // p = r / diag + beta p
-__global__ void __launch_bounds__(kThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                           const double* __restrict__ r, double* __restrict__ p, PcgScalars S) {
+__global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                              const double* __restrict__ r, double* __restrict__ p, PcgScalars S) {
     if (__ldcg(&S.n_active[1]) == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1] = __ldcg(&S.n_active[0]);   // p is dead once everything converged
-    LANE_SETUP();
+    VEC_SETUP();
     if (!live) return;
-    double be[3] = {__ldcg(&S.beta[b]), __ldcg(&S.beta[B + b]), __ldcg(&S.beta[2 * B + b])};
+    const double be = __ldcg(&S.beta[c * B + b]);
+#pragma unroll 2
     for (int f = row0; f < nf; f += rstride) {
-        double di = dinv[(size_t)f * B + b];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            size_t o = ((size_t)f * 3 + c) * B + b;
-            p[o] = r[o] * di + be[c] * p[o];
-        }
+        size_t o = ((size_t)f * 3 + c) * B + b;
+        p[o] = r[o] * dinv[(size_t)f * B + b] + be * p[o];
     }
 }
 
@@ -556,6 +671,22 @@ void last_pcg_iterations(int* fwd, int* adj) {
     if (adj) *adj = g_iters[1];
 }
 
+// One wave exactly: as many CTAs per chunk as the kernel's own occupancy allows (a 1.5-wave grid of
+// equal-work CTAs idles half the machine for a third of the time).
+template <typename Kernel>
+static LaneCfg one_wave(Kernel kernel, const LaneCfg& base, int rows, int threads) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    LaneCfg cfg = base;
+    int want = std::max(1, (sms * std::max(per_sm, 1)) / base.nchunks);
+    int rows_cta = threads == kVecThreads ? (kVecThreads >> base.shift) / 3 : (kThreads >> base.shift);
+    int most = (rows + rows_cta - 1) / rows_cta;
+    cfg.nslabs = std::max(1, std::min(std::min(want, most), 2048));
+    return cfg;
+}
+
 static int lane_config(int B, LaneCfg& cfg, int max_rows) {
     int shift = 0;
     while ((1 << shift) < B && shift < 5) ++shift;
@@ -670,15 +801,19 @@ static void prof_resolve(size_t used) {
     }
 }
 
-static int pcg_solve(const PlanDev& P, const LaneCfg& cfg, int B, PcgBuffers& w, const dfdm_options& opt, cudaStream_t st,
+static int pcg_solve(const PlanDev& P, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt, cudaStream_t st,
                      int32_t* host_flag, int* iters_out) {
+    const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
+    const LaneCfg cfg_spmv = one_wave(k_pcg_spmv, base, P.nf, kThreads);
+    const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
+    const LaneCfg cfg_dir = one_wave(k_pcg_direction, base, P.nf, kVecThreads);
     int grid = cfg.nchunks * cfg.nslabs;
     int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
     double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
     int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : 25;
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, sizeof(int32_t), st));      // snapshot: non-zero
-    k_pcg_init<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S);
+    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S);
     DFDM_LAUNCH_OK("k_pcg_init");
     int it = 0;
     while (it < maxiter) {
@@ -686,13 +821,13 @@ static int pcg_solve(const PlanDev& P, const LaneCfg& cfg, int B, PcgBuffers& w,
         size_t used = 0;
         prof_mark(st, -1, used);
         for (; it < stop; ++it) {
-            k_pcg_spmv<<<grid, kThreads, 0, st>>>(P, cfg, B, w.vals, w.p, w.Ap, w.S);
+            k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
             DFDM_LAUNCH_OK("k_pcg_spmv");
             prof_mark(st, 0, used);
-            k_pcg_update<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S, rtol * rtol);
+            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S, rtol * rtol);
             DFDM_LAUNCH_OK("k_pcg_update");
             prof_mark(st, 1, used);
-            k_pcg_direction<<<grid, kThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.p, w.S);
+            k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.p, w.S);
             DFDM_LAUNCH_OK("k_pcg_direction");
             prof_mark(st, 2, used);
         }

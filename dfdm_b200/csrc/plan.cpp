@@ -186,6 +186,18 @@ int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fix
         return (int)(std::lower_bound(b, e, col) - P.colidx.begin());
     };
 
+    // padded copy of the pattern for the SpMV kernels (indices depend on the row number only)
+    for (int f = 0; f < nf; ++f) P.ell_w = std::max(P.ell_w, P.rowptr[f + 1] - P.rowptr[f]);
+    P.ell_col.assign((size_t)nf * P.ell_w, 0);
+    P.ell_slot.assign((size_t)nf * P.ell_w, -1);
+    for (int f = 0; f < nf; ++f)
+        for (int u = 0; u < P.ell_w; ++u) {
+            int k = P.rowptr[f] + u;
+            bool real = k < P.rowptr[f + 1];
+            P.ell_col[(size_t)f * P.ell_w + u] = real ? P.colidx[k] : f;
+            P.ell_slot[(size_t)f * P.ell_w + u] = real ? k : -1;
+        }
+
     // per-edge scatter slots (uu, vv, uv, vu)
     P.edge_slots.assign(4 * (size_t)E, -1);
     for (int e = 0; e < E; ++e) {

@@ -22,6 +22,10 @@ struct PlanDev {
     const int32_t* rowptr = nullptr;      // [nf+1]
     const int32_t* colidx = nullptr;      // [nnz]
     const int32_t* diagslot = nullptr;    // [nf]
+    // the same pattern padded to ell_w entries per row: column (own row for padding); slots are rowptr[f] + u
+    int ell_w = 0;
+    const int32_t* ell_col = nullptr;     // [nf][ell_w]
+    const int32_t* ell_slot = nullptr;    // [nf][ell_w]
     // free-row incidence in free order: entry -> (edge, code) with code = CSR slot of the off-diagonal
     // (>= 0) or -1 - k when the neighbour is fixed node k (contributes to the right-hand side)
     const int32_t* finc_ptr = nullptr;    // [nf+1]
@@ -46,6 +50,8 @@ struct Plan {
     bool use_rcm = false;
     std::vector<int32_t> edges, free_nodes, fixed_nodes, freefixed, node_src;
     std::vector<int32_t> rowptr, colidx, diagslot, edge_slots;
+    int ell_w = 0;
+    std::vector<int32_t> ell_col, ell_slot;
     std::vector<int32_t> finc_ptr, finc_edge, finc_code;
     std::vector<int32_t> ninc_ptr, ninc_edge, ninc_sign;
     std::vector<int32_t> perm, pos;
