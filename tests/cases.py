@@ -202,3 +202,50 @@ def program_inputs(case):
                 params = list(target)
             goals.append((gkind, index, t, weight, params))
     return goals, terms, l2
+
+
+def goal_objects(case):
+    """Case term specs -> dfdm_b200 loss-term objects keyed by network keys (as a user of the reference API writes them)."""
+    from dfdm_b200 import goals as G
+    from dfdm_b200 import losses as L
+    net = case["network"]
+    index_key, index_uv = net.index_key(), net.index_uv()
+    terms = []
+    for kind, specs, alpha in case["terms"]:
+        if kind == "L2Regularizer":
+            terms.append(L.L2Regularizer(alpha))
+            continue
+        goals = []
+        for spec in specs:
+            gkind, index, target, weight = spec[:4]
+            key = None if index is None else (index_key[index] if gkind.startswith("Node") else index_uv[index])
+            if gkind == "EdgeVectorAngle":
+                goals.append(G.EdgeVectorAngleGoal(key, spec[4], target, weight))
+            elif gkind == "NetworkLoadPath":
+                goals.append(G.NetworkLoadPathGoal(target, weight))
+            else:
+                goals.append(getattr(G, gkind + "Goal")(key, target, weight))
+        terms.append(getattr(L, kind)(goals, alpha=alpha))
+    return terms
+
+
+def constraint_objects(case):
+    from dfdm_b200 import constraints as C
+    net = case["network"]
+    index_key, index_uv = net.index_key(), net.index_uv()
+    out = []
+    for spec in case.get("constraints", []):
+        kind = spec[0]
+        if kind == "EdgeLength":
+            out.append(C.EdgeLengthConstraint(index_uv[spec[1]], 0.0, 1.0))
+        elif kind == "EdgeVectorAngle":
+            out.append(C.EdgeVectorAngleConstraint(index_uv[spec[1]], spec[2], 0.0, 1.0))
+        elif kind == "NetworkEdgesLength":
+            out.append(C.NetworkEdgesLengthConstraint(0.0, 1.0))
+        elif kind == "NetworkEdgesForce":
+            out.append(C.NetworkEdgesForceConstraint(0.0, 1.0))
+        elif kind == "NodeNormalAngle":
+            out.append(C.NodeNormalAngleConstraint(index_key[spec[1]], [index_key[p] for p in spec[2]], spec[3], 0.0, 1.0))
+        elif kind == "NodeCurvature":
+            out.append(C.NodeCurvatureConstraint(index_key[spec[1]], [index_key[p] for p in spec[2]], 0.0, 1.0))
+    return out

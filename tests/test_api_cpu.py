@@ -1,0 +1,210 @@
+"""
+Host-side mirror of the reference API, no GPU needed: network stand-in, goal flattening, host goal
+inspection, constraint cotangents, recorder round trip, sharding helpers under gloo (world size 2).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cases import golden_cases, case_arrays, oracle_terms, program_inputs, goal_objects, constraint_objects
+from oracle import fdm_oracle as O
+from dfdm_b200.datastructures import FDNetwork
+from dfdm_b200.equilibrium import EquilibriumModel, EquilibriumState, network_updated
+from dfdm_b200.goals import goals_state
+from dfdm_b200.losses import Loss
+from dfdm_b200.optimization import OptimizationRecorder
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {c["name"]: c for c in golden_cases()}
+
+
+def _golden_state(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return g, EquilibriumState(g["xyz"], g["residuals"], g["vectors"], g["lengths"], g["forces"], g["q"])
+
+
+def test_network_orders_edges_by_first_endpoint_then_insertion():
+    net = FDNetwork()
+    for k in range(4):
+        net.add_node(x=float(k))
+    net.add_edge(2, 3)
+    net.add_edge(0, 1)
+    net.add_edge(0, 3)
+    net.add_edge(1, 2)
+    assert list(net.edges()) == [(0, 1), (0, 3), (1, 2), (2, 3)]
+    assert net.uv_index()[(0, 3)] == 1 and net.index_uv()[3] == (2, 3)
+    net.node_support(3)
+    assert list(net.nodes_free()) == [0, 1, 2] and list(net.nodes_fixed()) == [3]
+    net.edges_forcedensities(-1.5, keys=[(0, 1)])
+    assert net.edges_forcedensities() == [-1.5, 0.0, 0.0, 0.0]
+    net.nodes_loads([0.0, 0.0, -2.0], keys=[1])
+    assert net.node_load(1) == [0.0, 0.0, -2.0] and net.node_load(0) == [0.0, 0.0, 0.0]
+    copy = net.copy()
+    copy.node_attribute(0, "x", 9.0)
+    assert net.node_attribute(0, "x") == 0.0 and list(copy.edges()) == list(net.edges())
+
+
+def test_network_json_round_trip(tmp_path):
+    case = CASES["pringle"]
+    path = os.path.join(tmp_path, "net.json")
+    case["network"].to_json(path)
+    back = FDNetwork.from_json(path)
+    assert list(back.nodes()) == list(case["network"].nodes())
+    assert list(back.edges()) == list(case["network"].edges())
+    assert back.edges_forcedensities() == case["network"].edges_forcedensities()
+    assert list(back.nodes_fixed()) == list(case["network"].nodes_fixed())
+
+
+def test_from_lines_merges_end_points():
+    net = FDNetwork.from_lines([([0, 0, 0], [1, 0, 0]), ([1, 0, 0], [2, 0, 0]), ([2, 0, 0], [2, 1, 0])])
+    assert net.number_of_nodes() == 4 and list(net.edges()) == [(0, 1), (1, 2), (2, 3)]
+
+
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c["terms"]))
+def test_goal_objects_flatten_to_the_same_program(name):
+    case = CASES[name]
+    model = EquilibriumModel(case["network"])
+    loss = Loss(*goal_objects(case))
+    goals, terms, l2 = program_inputs(case)
+    flat = []
+    for t, term in enumerate(x for x in loss.loss_terms if hasattr(x, "goals")):
+        for goal in term.goals:
+            kind, index, weight, params = goal.record(model)
+            flat.append((kind, index, t, weight, [float(p) for p in params]))
+    assert len(flat) == len(goals)
+    for got, want in zip(flat, goals):
+        assert got[:4] == (want[0], want[1], want[2], float(want[3]))
+        assert np.allclose(got[4], np.asarray(want[4], dtype=np.float64).ravel())
+    prog = loss.program(model)
+    assert prog.n_goals == len(goals) and prog.n_terms == len(terms) and prog.l2_alpha == l2
+
+
+@pytest.mark.parametrize("name", ["mixed", "pringle", "arches10"])
+def test_host_goal_inspection_matches_oracle(name):
+    case = CASES[name]
+    g, eqstate = _golden_state(name)
+    model = EquilibriumModel(case["network"])
+    edges, is_fixed, xyz, loads = case_arrays(case)
+    s = O.Structure(len(is_fixed), edges, is_fixed)
+    ost = O.Model(s, loads, xyz[s.fixed_nodes])(g["q"])
+    for term_obj, term_spec in zip(goal_objects(case), oracle_terms(case)):
+        if term_spec[0] == "L2Regularizer":
+            continue
+        specs = [sp for sp in term_spec[1] if not (sp[0] == "NetworkLoadPath" and sp[2] is None)]
+        objs = [o for o, sp in zip(term_obj.goals, term_spec[1]) if not (sp[0] == "NetworkLoadPath" and sp[2] is None)]
+        gs = goals_state(objs, eqstate, model)
+        p, t, w = O.goals_state(specs, ost, O._NP)
+        assert np.allclose(gs.prediction, p, rtol=1e-13, atol=1e-15)
+        assert np.allclose(gs.target, t, rtol=1e-13, atol=1e-15)
+        assert np.array_equal(gs.weight, w)
+
+
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c.get("constraints")))
+def test_constraint_values_and_cotangents_match_reference(name):
+    """c(state) bit-close to the reference; cotangent rows pushed through the oracle's tape reproduce the golden Jacobians."""
+    case = CASES[name]
+    g, eqstate = _golden_state(name)
+    model = EquilibriumModel(case["network"])
+    edges, is_fixed, xyz, loads = case_arrays(case)
+    s = O.Structure(len(is_fixed), edges, is_fixed)
+    omodel = O.Model(s, loads, xyz[s.fixed_nodes])
+    for k, cons in enumerate(constraint_objects(case)):
+        value = np.atleast_1d(cons.constraint(eqstate, model))
+        assert np.allclose(value, g["constraint_%d" % k], rtol=1e-12, atol=1e-14)
+        cots = cons.cotangents(eqstate, model)
+        m = value.shape[0]
+        rows = [0, m // 2, m - 1] if m > 3 else range(m)
+        for r in rows:
+            ref = O.vjp(g["q"], omodel, {key: arr[r] for key, arr in cots.items()})
+            want = g["constraint_jac_%d" % k][r]
+            assert np.max(np.abs(ref - want)) <= 1e-9 * max(np.max(np.abs(want)), 1e-12)
+
+
+def test_network_update_writes_state_into_a_copy():
+    case = CASES["pillow"]
+    g, eqstate = _golden_state("pillow")
+    net = case["network"]
+    new = network_updated(net, eqstate)
+    assert new is not net
+    for idx, edge in new.index_uv().items():
+        assert new.edge_attribute(edge, "length") == g["lengths"][idx]
+        assert new.edge_attribute(edge, "force") == g["forces"][idx]
+        assert new.edge_forcedensity(edge) == g["q"][idx]
+    for idx, node in new.index_key().items():
+        assert new.node_coordinates(node) == g["xyz"][idx].tolist()
+        assert new.node_residual(node) == g["residuals"][idx].tolist()
+    assert abs(new.loadpath() - np.sum(np.abs(g["forces"] * g["lengths"]))) < 1e-9
+    assert net.node_coordinates(24) != new.node_coordinates(24)
+
+
+def test_recorder_round_trip(tmp_path):
+    rec = OptimizationRecorder()
+    for k in range(3):
+        rec(np.arange(4) * float(k))
+    path = os.path.join(tmp_path, "history.json")
+    rec.to_json(path)
+    back = OptimizationRecorder.from_json(path)
+    assert back.history == rec.history and len(back.history) == 3
+
+
+def test_model_without_gpu_raises_instead_of_falling_back():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    model = EquilibriumModel(CASES["pillow"]["network"])
+    assert model.structure.free_nodes == np.load(os.path.join(GOLDEN, "pillow.npz"))["free"].tolist()
+    with pytest.raises(RuntimeError):
+        model(CASES["pillow"]["q"])
+
+
+# ---- sharding under gloo, world size 2 ---------------------------------------------------------
+
+def _gloo_worker(rank, world, port, batch, tmpdir):
+    import torch
+    import torch.distributed as dist
+    from dfdm_b200.distributed import ShardedBatch, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    E = 5
+    q = torch.arange(batch * E, dtype=torch.float64).reshape(batch, E)
+
+    def evaluate(q_local):                      # stands in for Evaluator.loss_and_grad on this rank's GPU
+        return (q_local ** 2).sum(dim=1), 2.0 * q_local
+
+    sb = ShardedBatch(evaluate)
+    lo, hi = shard_bounds(batch, world, rank)
+    assert sb.local_slice(q).shape[0] == hi - lo
+    loss, dq = sb.loss_and_grad(q)
+    mean_loss, mean_dq = sb.ensemble(q)
+    torch.save({"loss": loss, "dq": dq, "mean_loss": mean_loss, "mean_dq": mean_dq}, os.path.join(tmpdir, "rank%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [8, 7])
+def test_sharded_batch_gathers_in_design_order(tmp_path, batch):
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    mp.spawn(_gloo_worker, args=(2, port, batch, str(tmp_path)), nprocs=2, join=True)
+    q = torch.arange(batch * 5, dtype=torch.float64).reshape(batch, 5)
+    for rank in range(2):
+        out = torch.load(os.path.join(tmp_path, "rank%d.pt" % rank))
+        assert torch.equal(out["loss"], (q ** 2).sum(dim=1))
+        assert torch.equal(out["dq"], 2.0 * q)
+        assert torch.allclose(out["mean_loss"], (q ** 2).sum(dim=1).mean())
+        assert torch.allclose(out["mean_dq"], (2.0 * q).mean(dim=0))
+
+
+def test_shard_bounds_cover_the_batch_exactly():
+    from dfdm_b200.distributed import shard_bounds
+    for batch in (1, 7, 8, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1

@@ -1,0 +1,155 @@
+"""
+The reference-facing Python API on the GPU: fdm(), EquilibriumModel, Loss, constraints and the
+optimiser loop, against golden vectors of the reference and against the same SciPy call fed by the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import Bounds, minimize
+
+from cases import golden_cases, case_arrays, oracle_terms, goal_objects, constraint_objects
+from oracle import fdm_oracle as O
+from dfdm_b200.equilibrium import EquilibriumModel, fdm, constrained_fdm
+from dfdm_b200.losses import Loss, SquaredError
+from dfdm_b200.goals import NodeResidualDirectionGoal
+from dfdm_b200.optimization import SLSQP, BFGS, TrustRegionConstrained, OptimizationRecorder, BatchedGradientDescent
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {c["name"]: c for c in golden_cases()}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _oracle_model(case):
+    edges, is_fixed, xyz, loads = case_arrays(case)
+    s = O.Structure(len(is_fixed), edges, is_fixed)
+    return O.Model(s, loads, xyz[s.fixed_nodes])
+
+
+@pytest.mark.parametrize("name", ["pillow", "dome", "arch200"])
+def test_fdm_updates_a_copy_of_the_network(name):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    net = case["network"].copy()
+    for edge, value in zip(list(net.edges()), g["q"]):
+        net.edge_forcedensity(edge, float(value))
+    eq = fdm(net)
+    assert eq is not net
+    xyz = np.asarray([eq.node_coordinates(k) for k in eq.nodes()])
+    assert _rel(xyz, g["xyz"]) < 1e-9
+    assert _rel(eq.edges_lengths(), g["lengths"]) < 1e-9 and _rel(eq.edges_forces(), g["forces"]) < 1e-9
+    assert abs(eq.loadpath() - np.sum(np.abs(g["forces"] * g["lengths"]))) < 1e-9 * max(1.0, eq.loadpath())
+
+
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c["terms"]))
+def test_loss_objects_match_reference(name):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = EquilibriumModel(case["network"])
+    loss = Loss(*goal_objects(case))
+    value = loss(g["q"], model)
+    assert isinstance(value, float) and abs(value - float(g["loss"])) <= 1e-9 * max(1.0, abs(float(g["loss"])))
+    v2, grad = loss.value_and_grad(g["q"], model)
+    assert abs(v2 - value) <= 1e-12 * max(1.0, abs(value)) and _rel(grad, g["grad"]) < 1e-7
+    # the terms evaluated one by one (examples/dome.py:298-306) add up to the loss
+    eqstate = model(g["q"])
+    parts = sum(term(eqstate, model) for term in loss.loss_terms)
+    assert abs(parts - value) <= 1e-9 * max(1.0, abs(value))
+
+
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c.get("constraints")))
+def test_constraints_and_jacobians_match_reference(name):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    model = EquilibriumModel(case["network"])
+    for k, cons in enumerate(constraint_objects(case)):
+        assert _rel(np.atleast_1d(cons(g["q"], model)), g["constraint_%d" % k]) < 1e-9
+        assert _rel(cons.jacobian(g["q"], model), g["constraint_jac_%d" % k]) < 1e-7
+
+
+def test_singular_network_raises_linalg_error():
+    from dfdm_b200.datastructures import FDNetwork
+    net = FDNetwork()
+    for k in range(4):
+        net.add_node(x=float(k))
+    for k in range(3):
+        net.add_edge(k, k + 1)
+    net.node_support(0)
+    net.node_support(3)
+    net.edges_forcedensities(0.0)        # getter: q stays 0 everywhere -> K = 0
+    with pytest.raises(np.linalg.LinAlgError):
+        fdm(net)
+
+
+def test_slsqp_follows_the_same_path_as_scipy_on_the_oracle():
+    """examples/arches.py: SLSQP with bounds (-inf, 0) on residual-direction goals."""
+    case = CASES["arches10"]
+    net = case["network"]
+    loss = Loss(*goal_objects(case))
+    recorder = OptimizationRecorder()
+    out = constrained_fdm(net, optimizer=SLSQP(disp=False), loss=loss, bounds=(-np.inf, 0.0), maxiter=200, tol=1e-9, callback=recorder)
+    q_opt = np.asarray(out.edges_forcedensities())
+    omodel = _oracle_model(case)
+    terms = oracle_terms(case)
+    q0 = np.asarray(net.edges_forcedensities(), dtype=np.float64)
+    ref = minimize(lambda x: O.loss_and_grad(terms, x, omodel), q0, jac=True, method="SLSQP", tol=1e-9,
+                   bounds=Bounds(-np.inf, 0.0), options={"maxiter": 200})
+    assert _rel(q_opt, ref.x) < 1e-5
+    model = EquilibriumModel(net)
+    assert loss(q_opt, model) < 1e-6 and loss(q_opt, model) <= loss(q0, model)
+    assert len(recorder.history) > 1
+    # the supports now pull along the target directions
+    res = np.asarray(out.node_residual(0))
+    assert np.allclose(res / np.linalg.norm(res), np.asarray([-1.0, 0.0, -0.4]) / np.linalg.norm([-1.0, 0.0, -0.4]), atol=1e-3)
+
+
+def test_bfgs_reduces_the_loss_and_constrained_slsqp_matches_scipy_on_the_oracle():
+    from scipy.optimize import NonlinearConstraint
+    case = CASES["pillow"]
+    net = case["network"].copy()
+    for edge, value in zip(list(net.edges()), case["q"]):
+        net.edge_forcedensity(edge, float(value))
+    loss = Loss(*goal_objects(case))
+    model = EquilibriumModel(net)
+    start = loss(case["q"], model)
+    q_bfgs = BFGS(disp=False).minimize(net, loss, maxiter=30, tol=1e-6, verbose=False)
+    assert loss(q_bfgs, model) < start
+    # examples/pillow.py: length and force constraints on every edge
+    cons = constraint_objects(case)[:2]
+    specs = case["constraints"][:2]
+    lengths = model(case["q"]).lengths
+    cons[0].bound_low, cons[0].bound_up = 0.9 * lengths.min(), 1.02 * lengths.max()
+    cons[1].bound_low, cons[1].bound_up = -100.0, -3.0
+    q_c = SLSQP(disp=False).minimize(net, loss, constraints=cons, maxiter=40, tol=1e-8, verbose=False)
+    omodel = _oracle_model(case)
+    terms = oracle_terms(case)
+    ocons = [NonlinearConstraint(fun=lambda x, sp=sp: O.constraint_jacobian(sp, x, omodel)[0],
+                                 jac=lambda x, sp=sp: O.constraint_jacobian(sp, x, omodel)[1], lb=c.bound_low, ub=c.bound_up)
+             for sp, c in zip(specs, cons)]
+    ref = minimize(lambda x: O.loss_and_grad(terms, x, omodel), case["q"], jac=True, method="SLSQP", tol=1e-8,
+                   bounds=Bounds(-np.inf, np.inf), constraints=ocons, options={"maxiter": 40})
+    assert _rel(q_c, ref.x) < 1e-4
+    state = model(q_c)
+    assert np.all(state.lengths >= cons[0].bound_low - 1e-6) and np.all(state.lengths <= cons[0].bound_up + 1e-6)
+    assert np.all(state.forces <= -3.0 + 1e-6)
+    # trust-constr runs through the same callbacks
+    q_t = TrustRegionConstrained(disp=False).minimize(net, loss, constraints=cons, maxiter=10, tol=1e-3, verbose=False)
+    assert np.all(np.isfinite(q_t)) and np.isfinite(loss(q_t, model))
+
+
+def test_batched_lockstep_descent_improves_every_design():
+    case = CASES["dome"]
+    model = EquilibriumModel(case["network"])
+    loss = Loss(*goal_objects(case))
+    rng = np.random.default_rng(3)
+    q0 = case["q"][None, :] * (1.0 + 0.1 * (rng.random((16, len(case["q"]))) - 0.5))
+    start = loss(q0, model)
+    q, value = BatchedGradientDescent(step=1e-1, maxiter=25).minimize(model, loss, q0, bounds=(None, -1e-3))
+    assert value.shape == (16,) and np.all(value <= start) and np.mean(value) < 0.7 * np.mean(start)
+    assert np.all(q <= -1e-3)
