@@ -382,6 +382,10 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library chatter (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -394,8 +398,10 @@ def main():
         import torch.distributed as dist
         if dist.is_initialized():
             dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
