@@ -230,7 +230,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter)
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond)
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -319,6 +319,7 @@ def gpu_arm(args, rank, world, local_rank):
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
+                       "preconditioner": ("multigrid V(1,1), %d levels" % (plan.info.get("mg_levels", 0) + 1)) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients)" % world,
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
                        "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
@@ -327,14 +328,18 @@ def gpu_arm(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h) * world, "api": "dfdm_loss_and_grad_host (pinned host buffers)"},
             "gpu_launches": launches}
     if solver == "pcg" and sum(prof_count) > 0:
-        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": 80.0 * nf * batch}
+        nc = plan.info.get("mg_n_coarse", 0)
+        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": 80.0 * nf * batch,
+               "k_mg_down[level 0]": (8.0 * nnz + 48.0 * nf + 24.0 * nc) * batch,
+               "k_mg_up[level 0]": (8.0 * nnz + 80.0 * nf + 24.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
         kernels = []
-        for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction")):
+        for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction", "k_mg_down[level 0]", "k_mg_up[level 0]",
+                                  "multigrid coarse levels (per V-cycle)")):
             if prof_count[k]:
                 avg_ms = prof_ms[k] / prof_count[k]
                 kernels.append({"kernel": name, "launches": prof_count[k], "avg_ms": avg_ms, "share_of_step": prof_ms[k] / ms_total,
                                 "algorithmic_bytes": alg[name], "achieved_gbs": alg[name] / (avg_ms * 1e-3) / 1e9})
-        top = max(kernels, key=lambda kk: kk["share_of_step"])
+        top = max((kk for kk in kernels if kk["algorithmic_bytes"] > 0), key=lambda kk: kk["share_of_step"])
         line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
                             "frac": top["achieved_gbs"] / peak, "traffic": traffic_for(top["kernel"], wl["name"]),
                             "peak_source": peak_src, "timing": "CUDA events on the launch stream after every PCG launch, timed region"}
@@ -379,6 +384,7 @@ def main():
     ap.add_argument("--pcg-rtol", type=float, default=0.0)
     ap.add_argument("--pcg-check-every", type=int, default=0)
     ap.add_argument("--pcg-maxiter", type=int, default=0, help="cap PCG iterations (kernel tuning runs only: results not converged)")
+    ap.add_argument("--precond", default="auto", choices=["auto", "jacobi", "multigrid"])
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

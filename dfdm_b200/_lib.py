@@ -18,6 +18,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 STATUS_OK, STATUS_SINGULAR, STATUS_NOT_CONVERGED, STATUS_NONFINITE = 0, 1, 2, 3
 SOLVER_AUTO, SOLVER_DIRECT, SOLVER_PCG = 0, 1, 2
 SOLVERS = {"auto": SOLVER_AUTO, "direct": SOLVER_DIRECT, "pcg": SOLVER_PCG}
+PRECONDS = {"auto": 0, "jacobi": 1, "multigrid": 2}
 
 ARR_FREE, ARR_FIXED, ARR_FREEFIXED, ARR_ROWPTR, ARR_COLIDX, ARR_EDGE_SLOTS, ARR_SOLVER_PERM = range(7)
 ARR_NODE_INC_PTR, ARR_NODE_INC_EDGE, ARR_NODE_INC_SIGN = 7, 8, 9
@@ -37,14 +38,14 @@ SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan
 
 class Options(C.Structure):
     _fields_ = [("solver", C.c_int32), ("pcg_maxiter", C.c_int32), ("pcg_rtol", C.c_double),
-                ("pcg_check_every", C.c_int32), ("reserved", C.c_int32)]
+                ("pcg_check_every", C.c_int32), ("pcg_precond", C.c_int32)]
 
 
 class PlanInfo(C.Structure):
     _fields_ = [("n", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32), ("n_fixed", C.c_int32),
                 ("nnz", C.c_int32), ("bandwidth_natural", C.c_int32), ("bandwidth_solver", C.c_int32),
                 ("direct_fits", C.c_int32), ("direct_smem_bytes", C.c_int64), ("auto_solver", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("mg_levels", C.c_int32), ("mg_n_coarse", C.c_int32), ("mg_n_coarsest", C.c_int32)]
 
 
 class DfdmError(RuntimeError):
@@ -97,10 +98,12 @@ def check(rc):
         raise DfdmError("dfdm_b200 error %d: %s" % (rc, (lib.dfdm_last_error() or b"").decode()))
 
 
-def make_options(solver="auto", pcg_maxiter=0, pcg_rtol=0.0, pcg_check_every=0):
+def make_options(solver="auto", pcg_maxiter=0, pcg_rtol=0.0, pcg_check_every=0, pcg_precond="auto"):
     if isinstance(solver, str):
         solver = SOLVERS[solver]
-    return Options(solver, int(pcg_maxiter), float(pcg_rtol), int(pcg_check_every), 0)
+    if isinstance(pcg_precond, str):
+        pcg_precond = PRECONDS[pcg_precond]
+    return Options(solver, int(pcg_maxiter), float(pcg_rtol), int(pcg_check_every), int(pcg_precond))
 
 
 def plan_array(handle, which):
@@ -128,7 +131,7 @@ def profile_enable(on=True):
 
 
 def profile_read():
-    ms = (C.c_double * 4)()
-    count = (C.c_int64 * 4)()
+    ms = (C.c_double * 8)()
+    count = (C.c_int64 * 8)()
     lib.dfdm_profile_read(ms, count)
     return list(ms), list(count)

@@ -47,6 +47,41 @@ static int upload_plan(const Plan& P, int device, PlanDev& out) {
     return DFDM_OK;
 }
 
+static int upload_mg(const Plan& P, int device, MgDev& out) {
+    std::lock_guard<std::mutex> lock(P.mu);
+    auto it = P.mg_dev.find(device);
+    if (it != P.mg_dev.end()) {
+        out = it->second;
+        return DFDM_OK;
+    }
+    MgDev M;
+    M.n_levels = (int)P.mg.size();
+    for (int l = 0; l < M.n_levels; ++l) {
+        const MgLevel& L = P.mg[l];
+        const std::vector<int32_t>* arrays[] = {&L.agg, &L.mem_ptr, &L.mem_idx, &L.rowptr, &L.ell_col, &L.diagslot, &L.gal_ptr, &L.gal_src};
+        constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
+        int64_t offs[NA], total = 0;
+        for (int k = 0; k < NA; ++k) {
+            offs[k] = total;
+            total += ((int64_t)arrays[k]->size() * 4 + 255) & ~(int64_t)255;
+        }
+        char* block = nullptr;
+        DFDM_CUDA_OK(cudaMalloc(&block, (size_t)std::max<int64_t>(total, 256)));
+        for (int k = 0; k < NA; ++k)
+            if (!arrays[k]->empty())
+                DFDM_CUDA_OK(cudaMemcpy(block + offs[k], arrays[k]->data(), arrays[k]->size() * 4, cudaMemcpyHostToDevice));
+        auto at = [&](int k) { return reinterpret_cast<const int32_t*>(block + offs[k]); };
+        MgLevelDev& D = M.lv[l];
+        D.n_fine = L.n_fine; D.n = L.n; D.nnz = L.nnz; D.ell_w = L.ell_w;
+        D.agg = at(0); D.mem_ptr = at(1); D.mem_idx = at(2); D.rowptr = at(3); D.ell_col = at(4); D.diagslot = at(5);
+        D.gal_ptr = at(6); D.gal_src = at(7);
+        P.dev_block[1000 * (l + 1) + device] = block;     // freed with the plan (key unique per level and device)
+    }
+    P.mg_dev[device] = M;
+    out = M;
+    return DFDM_OK;
+}
+
 static int upload_prog(const GoalProg& G, int device, GoalProgDev& out) {
     std::lock_guard<std::mutex> lock(G.mu);
     auto it = G.dev.find(device);
@@ -109,6 +144,8 @@ static int dispatch(const dfdm_plan* plan, const dfdm_goalprog* prog, Eval& ev, 
     DFDM_CUDA_OK(cudaGetDevice(&device));
     int rc = upload_plan(*plan, device, ev.P);
     if (rc) return rc;
+    rc = upload_mg(*plan, device, ev.M);
+    if (rc) return rc;
     ev.has_prog = prog != nullptr;
     if (prog) {
         rc = upload_prog(*prog, device, ev.G);
@@ -163,7 +200,7 @@ void dfdm_plan_destroy(dfdm_plan* plan) {
     for (auto& kv : plan->dev_block) {
         int prev = 0;
         cudaGetDevice(&prev);
-        cudaSetDevice(kv.first);
+        cudaSetDevice(kv.first % 1000);
         cudaFree(kv.second);
         cudaSetDevice(prev);
     }
@@ -408,10 +445,10 @@ void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters) {
 void dfdm_profile_enable(int32_t on) { profile_enable(on); }
 
 void dfdm_profile_read(double* ms, int64_t* count) {
-    double m[4];
-    long long c[4];
+    double m[8];
+    long long c[8];
     profile_read(m, c);
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
         if (ms) ms[k] = m[k];
         if (count) count[k] = (int64_t)c[k];
     }

@@ -36,6 +36,7 @@ extern std::atomic<long long> g_launches;
 // One evaluation request, resolved to device pointers.  All batch arrays are design-major.
 struct Eval {
     PlanDev P;
+    MgDev M;
     GoalProgDev G;
     bool has_prog = false;
     bool adjoint = false;          // compute dq

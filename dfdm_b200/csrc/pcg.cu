@@ -223,7 +223,7 @@ __device__ bool publish_vec(const double (&v)[NV], const LaneCfg& cfg, int B, do
 // x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                          const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
-                                                         PcgScalars S) {
+                                                         PcgScalars S, int mg) {
     VEC_SETUP();
     double v[2] = {0, 0};
     if (live) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
             double rc = r[o];
             double z = rc * dinv[(size_t)f * B + b];
             x[o] = 0.0;
-            p[o] = z;
+            p[o] = mg ? 0.0 : z;             // multigrid: the first direction comes from the V-cycle
             v[0] += rc * z;
             v[1] += rc * rc;
         }
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
             S.bb[cc * B + b2] = bb;
             S.beta[cc * B + b2] = 0.0;
             int frozen = (bb == 0.0 || !(rho != 0.0)) ? 1 : 0;     // zero right-hand side: x = 0 is exact
+            (void)mg;
             S.frozen[cc * B + b2] = frozen;
             fresh += frozen ? 0 : 1;
         }
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
                                                                               const double* __restrict__ dinv,
                                                                               const double* __restrict__ p,
                                                                               const double* __restrict__ Ap, double* __restrict__ x,
-                                                                              double* __restrict__ r, PcgScalars S, double tol2) {
+                                                                              double* __restrict__ r, PcgScalars S, double tol2, int mg) {
     // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
     if (__ldcg(&S.n_active[1]) == 0) return;
     VEC_SETUP();
@@ -397,11 +398,13 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
             if (S.frozen[o]) { S.beta[o] = 0.0; continue; }
             double rho_new = sum_slabs<6>(S.partial, cc, b2, B, cfg.nslabs);
             double rr = sum_slabs<6>(S.partial, 3 + cc, b2, B, cfg.nslabs);
-            double rho_old = S.rho[o];
-            double be = rho_old != 0.0 ? rho_new / rho_old : 0.0;
-            if (!isfinite(be)) be = 0.0;
-            S.beta[o] = be;
-            S.rho[o] = rho_new;
+            if (!mg) {                           // Jacobi: z = r / diag was formed here; multigrid: beta comes from the V-cycle
+                double rho_old = S.rho[o];
+                double be = rho_old != 0.0 ? rho_new / rho_old : 0.0;
+                if (!isfinite(be)) be = 0.0;
+                S.beta[o] = be;
+                S.rho[o] = rho_new;
+            }
             if (!isfinite(rr)) {
                 S.frozen[o] = 2;                 // breakdown: reported as DFDM_STATUS_NONFINITE
                 done += 1;
@@ -416,7 +419,8 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
 
 // p = r / diag + beta p
 __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                              const double* __restrict__ r, double* __restrict__ p, PcgScalars S) {
+                                                              const double* __restrict__ r, const double* __restrict__ z,
+                                                              double* __restrict__ p, PcgScalars S) {
     if (__ldcg(&S.n_active[1]) == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1] = __ldcg(&S.n_active[0]);   // p is dead once everything converged
     VEC_SETUP();
@@ -425,8 +429,262 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg c
 #pragma unroll 2
     for (int f = row0; f < nf; f += rstride) {
         size_t o = ((size_t)f * 3 + c) * B + b;
-        p[o] = r[o] * dinv[(size_t)f * B + b] + be * p[o];
+        double zc = z ? z[o] : r[o] * dinv[(size_t)f * B + b];
+        p[o] = zc + be * p[o];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Aggregation multigrid V(1,1)-cycle as the CG preconditioner (z = M r).
+//
+// Levels: 0 = K itself; level l+1 = Galerkin product of level l with piecewise-constant prolongation
+// over plan-time aggregates (<= 4 rows).  Per level, with b the level's right-hand side:
+//   down:  x = w D^-1 b (damped Jacobi from a zero guess, never stored);  t = (K D^-1) b;
+//          residual b - w t restricted (summed over each aggregate) into the coarse right-hand side
+//   up:    x' = w D^-1 b + s P e            (e = coarse solution, s = over-correction for plain aggregation)
+//          z  = x' + w D^-1 (b - K x') with K x' = w t + s K P e
+// Both passes stream one copy of the matrix (down: the column-scaled K D^-1; up: K) and gather one
+// vector, like the plain SpMV.  Pre- and post-smoother are the same symmetric sweep and the coarse
+// correction is scaled by a constant, so M is symmetric positive definite whenever K is definite.
+// ------------------------------------------------------------------------------------------------
+
+struct MgMat {                 // one level's operator (level 0: the plan's CSR)
+    int n, ell_w;
+    const int32_t* rowptr;
+    const int32_t* ell_col;
+    const double* vals;        // K          [nnz][B]
+    const double* vals_s;      // K D^-1     [nnz][B]
+    const double* dinv;        // 1 / diag   [n][B]
+};
+
+constexpr double kMgOmega = 0.8;
+constexpr double kMgOver = 1.5;
+
+// coarse operator values: sum of the fine values feeding each coarse slot, then 1 / diagonal
+__global__ void __launch_bounds__(kThreads) k_mg_galerkin(MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ vals_f,
+                                                         double* __restrict__ vals_c) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int s = row0; s < L.nnz; s += rstride) {
+        double acc = 0.0;
+        for (int k = L.gal_ptr[s]; k < L.gal_ptr[s + 1]; ++k) acc += vals_f[(size_t)L.gal_src[k] * B + b];
+        vals_c[(size_t)s * B + b] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_mg_dinv(int n, const int32_t* __restrict__ diagslot, LaneCfg cfg, int B,
+                                                     const double* __restrict__ vals, double* __restrict__ dinv) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int f = row0; f < n; f += rstride) dinv[(size_t)f * B + b] = 1.0 / vals[(size_t)diagslot[f] * B + b];
+}
+
+// vals_s[k] = vals[k] * dinv[col(k)]
+__global__ void __launch_bounds__(kThreads) k_mg_scale(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col,
+                                                      int W, LaneCfg cfg, int B, const double* __restrict__ vals,
+                                                      const double* __restrict__ dinv, double* __restrict__ vals_s) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int f = row0; f < n; f += rstride) {
+        int k0 = rowptr[f], len = rowptr[f + 1] - k0;
+        for (int u = 0; u < len; ++u)
+            vals_s[(size_t)(k0 + u) * B + b] = vals[(size_t)(k0 + u) * B + b] * dinv[(size_t)ell_col[(size_t)f * W + u] * B + b];
+    }
+}
+
+// row product helper: acc[c] = sum_u val[k0+u] * vec[col(u)][c]
+__device__ __forceinline__ void mg_row(const int32_t* __restrict__ ell_col, int W, int f, int k0, int len, const double* __restrict__ vb,
+                                       const double* __restrict__ xb, size_t sB, double acc[3]) {
+    constexpr int U = 5;
+    for (int u0 = 0; u0 < len; u0 += U) {
+        int col[U];
+        double a[U], x0[U], x1[U], x2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) col[u] = ell_col[(size_t)f * W + min(u0 + u, len - 1)];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = u0 + u < len ? vb[(size_t)(k0 + u0 + u) * sB] : 0.0;
+            const double* xj = xb + (size_t)col[u] * 3 * sB;
+            x0[u] = xj[0];
+            x1[u] = xj[sB];
+            x2[u] = xj[2 * sB];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc[0] += a[u] * x0[u];
+            acc[1] += a[u] * x1[u];
+            acc[2] += a[u] * x2[u];
+        }
+    }
+}
+
+// down pass of level l (operator A, right-hand side bvec): writes t = (K D^-1) b and the coarse right-hand side.
+// One thread per (coarse row, design): it owns the aggregate, so the restriction needs no atomics.
+__global__ void __launch_bounds__(kThreads, 3) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
+                                                        double* __restrict__ t, double* __restrict__ b_coarse,
+                                                        const int32_t* __restrict__ n_active) {
+    if (__ldcg(&n_active[1]) == 0) return;
+    LANE_SETUP();
+    if (!live) return;
+    const size_t sB = (size_t)B;
+    for (int I = row0; I < L.n; I += rstride) {
+        double rc[3] = {0.0, 0.0, 0.0};
+        for (int m = L.mem_ptr[I]; m < L.mem_ptr[I + 1]; ++m) {
+            int f = L.mem_idx[m];
+            int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+            double acc[3] = {0.0, 0.0, 0.0};
+            mg_row(A.ell_col, A.ell_w, f, k0, len, A.vals_s + b, bvec + b, sB, acc);
+            size_t o = (size_t)f * 3 * sB + b;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                t[o + c * sB] = acc[c];
+                rc[c] += bvec[o + c * sB] - kMgOmega * acc[c];
+            }
+        }
+        size_t oc = (size_t)I * 3 * sB + b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b_coarse[oc + c * sB] = rc[c];
+    }
+}
+
+// up pass of level l: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
+__global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
+                                                      const double* __restrict__ t, const double* __restrict__ e_coarse,
+                                                      double* __restrict__ z, PcgScalars S, int dots, int first) {
+    if (__ldcg(&S.n_active[1]) == 0) return;
+    LANE_SETUP();
+    double v[3] = {0, 0, 0};
+    if (live) {
+        const size_t sB = (size_t)B;
+        for (int f = row0; f < A.n; f += rstride) {
+            int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+            // s = (K P e)_f: gather the coarse solution through the aggregate map
+            double sacc[3] = {0.0, 0.0, 0.0};
+            constexpr int U = 5;
+            for (int u0 = 0; u0 < len; u0 += U) {
+                int cg[U];
+                double a[U], x0[U], x1[U], x2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) cg[u] = L.agg[A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)]];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    a[u] = u0 + u < len ? A.vals[(size_t)(k0 + u0 + u) * sB + b] : 0.0;
+                    const double* ej = e_coarse + (size_t)cg[u] * 3 * sB + b;
+                    x0[u] = ej[0];
+                    x1[u] = ej[sB];
+                    x2[u] = ej[2 * sB];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    sacc[0] += a[u] * x0[u];
+                    sacc[1] += a[u] * x1[u];
+                    sacc[2] += a[u] * x2[u];
+                }
+            }
+            const double wd = kMgOmega * A.dinv[(size_t)f * sB + b];
+            const double* ei = e_coarse + (size_t)L.agg[f] * 3 * sB + b;
+            size_t o = (size_t)f * 3 * sB + b;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double bc = bvec[o + c * sB];
+                double xn = wd * bc + kMgOver * ei[c * sB];
+                double zc = xn + wd * (bc - kMgOmega * t[o + c * sB] - kMgOver * sacc[c]);
+                z[o + c * sB] = zc;
+                v[c] += bc * zc;
+            }
+        }
+    }
+    if (!dots) return;
+    if (publish_partials<3>(v, cfg, B, S.partial, S.tickets)) {
+        for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
+            int cc = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+            if (b2 >= B) continue;
+            int o = cc * B + b2;
+            double rho_new = sum_slabs<3>(S.partial, cc, b2, B, cfg.nslabs);
+            double rho_old = S.rho[o];
+            double be = (!first && rho_old != 0.0) ? rho_new / rho_old : 0.0;
+            if (!isfinite(be) || S.frozen[o]) be = 0.0;
+            S.beta[o] = be;
+            if (!S.frozen[o] || first) S.rho[o] = rho_new;
+        }
+    }
+}
+
+// coarsest level: dense LDL^T per design, interleaved storage Lf[(i(i+1)/2 + j)][B]; one thread per design
+__global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col, int W, int B,
+                                     const double* __restrict__ vals, double* __restrict__ Lf) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t sB = (size_t)B;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        int k0 = rowptr[i], len = rowptr[i + 1] - k0;
+        for (int u = 0; u < len; ++u) {
+            int j = ell_col[(size_t)i * W + u];
+            if (j <= i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = vals[(size_t)(k0 + u) * sB + b];
+        }
+    }
+    // right-looking LDL^T in place: strictly lower part ends up holding L, the diagonal D
+    for (int j = 0; j < n; ++j) {
+        const double inv = 1.0 / Lf[(size_t)(j * (j + 1) / 2 + j) * sB + b];
+        for (int i = j + 1; i < n; ++i) {
+            const double lij = Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * inv;
+            for (int k = j + 1; k <= i; ++k)
+                Lf[(size_t)(i * (i + 1) / 2 + k) * sB + b] -= lij * Lf[(size_t)(k * (k + 1) / 2 + j) * sB + b];   // column j still unscaled
+        }
+        for (int i = j + 1; i < n; ++i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] *= inv;
+    }
+}
+
+// coarsest solve: e = K_c^-1 b for the three coordinates; one thread per (coordinate, design)
+__global__ void k_mg_coarsest_solve(int n, int B, const double* __restrict__ Lf, const double* __restrict__ bvec, double* __restrict__ e,
+                                    const int32_t* __restrict__ n_active) {
+    if (__ldcg(&n_active[1]) == 0) return;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * B) return;
+    int c = idx / B, b = idx - c * B;
+    const size_t sB = (size_t)B;
+    // forward: L y = b (y stored in e)
+    for (int i = 0; i < n; ++i) {
+        double yi = bvec[((size_t)i * 3 + c) * sB + b];
+        for (int j = 0; j < i; ++j) yi -= Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * e[((size_t)j * 3 + c) * sB + b];
+        e[((size_t)i * 3 + c) * sB + b] = yi;
+    }
+    for (int i = 0; i < n; ++i) e[((size_t)i * 3 + c) * sB + b] /= Lf[(size_t)(i * (i + 1) / 2 + i) * sB + b];
+    for (int i = n - 1; i >= 0; --i) {
+        double xi = e[((size_t)i * 3 + c) * sB + b];
+        for (int j = i + 1; j < n; ++j) xi -= Lf[(size_t)(j * (j + 1) / 2 + i) * sB + b] * e[((size_t)j * 3 + c) * sB + b];
+        e[((size_t)i * 3 + c) * sB + b] = xi;
+    }
+}
+
+// coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
+__global__ void k_mg_coarsest_jacobi(MgMat A, int B, int sweeps, const double* __restrict__ bvec, double* __restrict__ e,
+                                     double* __restrict__ tmp, const int32_t* __restrict__ n_active) {
+    if (__ldcg(&n_active[1]) == 0) return;
+    // one CTA per design (all rows, three coordinates): rows in a loop, sweeps separated by block barriers
+    int b = blockIdx.x;
+    if (b >= B) return;
+    const size_t sB = (size_t)B;
+    for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) e[(size_t)i * sB + b] = kMgOmega * A.dinv[(size_t)(i / 3) * sB + b] * bvec[(size_t)i * sB + b];
+    __syncthreads();
+    double* src = e;
+    double* dst = tmp;
+    for (int s = 0; s < sweeps; ++s) {
+        for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) {
+            int f = i / 3, c = i - f * 3;
+            int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+            double acc = 0.0;
+            for (int u = 0; u < len; ++u)
+                acc += A.vals[(size_t)(k0 + u) * sB + b] * src[((size_t)A.ell_col[(size_t)f * A.ell_w + u] * 3 + c) * sB + b];
+            dst[(size_t)i * sB + b] = src[(size_t)i * sB + b] + kMgOmega * A.dinv[(size_t)f * sB + b] * (bvec[(size_t)i * sB + b] - acc);
+        }
+        __syncthreads();
+        double* sw = src; src = dst; dst = sw;
+    }
+    if (src != e)
+        for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) e[(size_t)i * sB + b] = src[(size_t)i * sB + b];
 }
 
 // status: not converged if any coordinate of the design is still active
@@ -704,7 +962,22 @@ static int lane_config(int B, LaneCfg& cfg, int max_rows) {
     return DFDM_OK;
 }
 
+constexpr int kCoarsestDense = 48;     // dense LDL^T on the coarsest level up to this many rows
+
+struct MgBuffers {
+    int n_levels = 0;                                  // coarse levels in use
+    double* vals[kMaxMgLevels + 1] = {nullptr};
+    double* vals_s[kMaxMgLevels + 1] = {nullptr};
+    double* dinv[kMaxMgLevels + 1] = {nullptr};
+    double* b[kMaxMgLevels + 1] = {nullptr};
+    double* t[kMaxMgLevels + 1] = {nullptr};
+    double* z[kMaxMgLevels + 1] = {nullptr};
+    double* Lf = nullptr;
+    double* tmp = nullptr;
+};
+
 struct PcgBuffers {
+    MgBuffers mg;
     double *qT, *vals, *dinv, *xs, *r, *p, *Ap;
     double *X, *R, *U, *L, *F, *Xb, *Rb, *Ub, *dqT;
     double *cX, *cR, *cU, *cL, *cF;
@@ -714,7 +987,24 @@ struct PcgBuffers {
 };
 
 static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int64_t B, int nslabs_max,
-                  int nchunks_max, PcgBuffers& w) {
+                  int nchunks_max, PcgBuffers& w, int mg_levels, const int* mg_n, const int* mg_nnz) {
+    w.mg.n_levels = mg_levels;
+    if (mg_levels > 0) {
+        w.mg.vals_s[0] = bump.take<double>(nnz * B);
+        w.mg.z[0] = bump.take<double>(nf * 3 * B);
+        for (int l = 1; l <= mg_levels; ++l) {
+            int64_t nl = mg_n[l - 1], zl = mg_nnz[l - 1];
+            w.mg.vals[l] = bump.take<double>(zl * B);
+            w.mg.vals_s[l] = bump.take<double>(zl * B);
+            w.mg.dinv[l] = bump.take<double>(nl * B);
+            w.mg.b[l] = bump.take<double>(nl * 3 * B);
+            w.mg.t[l] = bump.take<double>(nl * 3 * B);
+            w.mg.z[l] = bump.take<double>(nl * 3 * B);
+        }
+        int64_t nc = mg_n[mg_levels - 1];
+        if (nc <= kCoarsestDense) w.mg.Lf = bump.take<double>(nc * (nc + 1) / 2 * B);
+        else w.mg.tmp = bump.take<double>(nc * 3 * B);
+    }
     w.qT = bump.take<double>(E * B);
     w.vals = bump.take<double>(nnz * B);
     w.dinv = bump.take<double>(nf * B);
@@ -757,7 +1047,9 @@ static constexpr int kMaxSlabs = 2048;
 int64_t pcg_workspace(const Plan& P, int B) {
     Bump bump(nullptr);
     PcgBuffers w{};
-    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w);
+    int mn[kMaxMgLevels], mz[kMaxMgLevels];
+    for (size_t l = 0; l < P.mg.size(); ++l) { mn[l] = P.mg[l].n; mz[l] = P.mg[l].nnz; }
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, (int)P.mg.size(), mn, mz);
     return bump.off;
 }
 
@@ -767,17 +1059,17 @@ struct Profile {
     bool on = false;
     std::vector<cudaEvent_t> ev;
     std::vector<int> kind;
-    double ms[4] = {0, 0, 0, 0};
-    long long count[4] = {0, 0, 0, 0};
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 static Profile g_prof;
 
 void profile_enable(int on) {
     g_prof.on = on != 0;
-    for (int k = 0; k < 4; ++k) { g_prof.ms[k] = 0.0; g_prof.count[k] = 0; }
+    for (int k = 0; k < 8; ++k) { g_prof.ms[k] = 0.0; g_prof.count[k] = 0; }
 }
 void profile_read(double* ms, long long* count) {
-    for (int k = 0; k < 4; ++k) { ms[k] = g_prof.ms[k]; count[k] = g_prof.count[k]; }
+    for (int k = 0; k < 8; ++k) { ms[k] = g_prof.ms[k]; count[k] = g_prof.count[k]; }
 }
 static void prof_mark(cudaStream_t st, int kind, size_t& used) {
     if (!g_prof.on) return;
@@ -801,8 +1093,86 @@ static void prof_resolve(size_t used) {
     }
 }
 
-static int pcg_solve(const PlanDev& P, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt, cudaStream_t st,
-                     int32_t* host_flag, int* iters_out) {
+// grid for a 256-thread row kernel over `rows` rows: one wave of that kernel
+template <typename Kernel>
+static LaneCfg rows_cfg(Kernel kernel, const LaneCfg& base, int rows) { return one_wave(kernel, base, rows, kThreads); }
+
+static MgMat mg_mat(const PlanDev& P, const MgDev& M, const PcgBuffers& w, int level) {
+    MgMat A{};
+    if (level == 0) {
+        A.n = P.nf; A.ell_w = P.ell_w; A.rowptr = P.rowptr; A.ell_col = P.ell_col;
+        A.vals = w.vals; A.dinv = w.dinv;
+    } else {
+        const MgLevelDev& L = M.lv[level - 1];
+        A.n = L.n; A.ell_w = L.ell_w; A.rowptr = L.rowptr; A.ell_col = L.ell_col;
+        A.vals = w.mg.vals[level]; A.dinv = w.mg.dinv[level];
+    }
+    A.vals_s = w.mg.vals_s[level];
+    return A;
+}
+
+// numerical set-up of the hierarchy for the assembled K of this evaluation (once per evaluation)
+static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, cudaStream_t st) {
+    const int nl = M.n_levels;
+    for (int l = 0; l < nl; ++l) {
+        const MgLevelDev& L = M.lv[l];
+        MgMat Af = mg_mat(P, M, w, l);
+        LaneCfg c1 = rows_cfg(k_mg_scale, base, Af.n);
+        k_mg_scale<<<c1.nchunks * c1.nslabs, kThreads, 0, st>>>(Af.n, Af.rowptr, Af.ell_col, Af.ell_w, c1, B, Af.vals, Af.dinv,
+                                                                 w.mg.vals_s[l]);
+        DFDM_LAUNCH_OK("k_mg_scale");
+        LaneCfg c2 = rows_cfg(k_mg_galerkin, base, L.nnz);
+        k_mg_galerkin<<<c2.nchunks * c2.nslabs, kThreads, 0, st>>>(L, c2, B, Af.vals, w.mg.vals[l + 1]);
+        DFDM_LAUNCH_OK("k_mg_galerkin");
+        LaneCfg c3 = rows_cfg(k_mg_dinv, base, L.n);
+        k_mg_dinv<<<c3.nchunks * c3.nslabs, kThreads, 0, st>>>(L.n, L.diagslot, c3, B, w.mg.vals[l + 1], w.mg.dinv[l + 1]);
+        DFDM_LAUNCH_OK("k_mg_dinv");
+    }
+    const MgLevelDev& C = M.lv[nl - 1];
+    if (w.mg.Lf) {
+        k_mg_coarsest_factor<<<(B + 63) / 64, 64, 0, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.Lf);
+        DFDM_LAUNCH_OK("k_mg_coarsest_factor");
+    }
+    return DFDM_OK;
+}
+
+// z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
+static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
+                     size_t& used) {
+    const int nl = M.n_levels;
+    w.mg.b[0] = w.r;
+    w.mg.t[0] = w.Ap;           // Ap is dead between the update and the next SpMV
+    for (int l = 0; l < nl; ++l) {
+        MgMat A = mg_mat(P, M, w, l);
+        LaneCfg c = rows_cfg(k_mg_down, base, M.lv[l].n);
+        k_mg_down<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active);
+        DFDM_LAUNCH_OK("k_mg_down");
+        if (l == 0) prof_mark(st, 3, used);
+    }
+    const MgLevelDev& C = M.lv[nl - 1];
+    if (w.mg.Lf) {
+        k_mg_coarsest_solve<<<(3 * B + 63) / 64, 64, 0, st>>>(C.n, B, w.mg.Lf, w.mg.b[nl], w.mg.z[nl], w.S.n_active);
+        DFDM_LAUNCH_OK("k_mg_coarsest_solve");
+    } else {
+        MgMat A = mg_mat(P, M, w, nl);
+        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active);
+        DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
+    }
+    for (int l = nl - 1; l >= 0; --l) {
+        MgMat A = mg_mat(P, M, w, l);
+        LaneCfg c = rows_cfg(k_mg_up, base, A.n);
+        if (l == 0) prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
+        k_mg_up<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
+                                                          l == 0 ? 1 : 0, first);
+        DFDM_LAUNCH_OK("k_mg_up");
+        if (l == 0) prof_mark(st, 4, used);
+    }
+    return DFDM_OK;
+}
+
+static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
+                     cudaStream_t st, int32_t* host_flag, int* iters_out) {
+    const bool mg = M != nullptr && M->n_levels > 0;
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
     const LaneCfg cfg_spmv = one_wave(k_pcg_spmv, base, P.nf, kThreads);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
@@ -810,11 +1180,18 @@ static int pcg_solve(const PlanDev& P, const LaneCfg& base, int B, PcgBuffers& w
     int grid = cfg.nchunks * cfg.nslabs;
     int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
     double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
-    int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : 25;
+    int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : (mg ? 5 : 25);
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, sizeof(int32_t), st));      // snapshot: non-zero
-    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S);
+    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0);
     DFDM_LAUNCH_OK("k_pcg_init");
+    size_t used0 = 0;
+    if (mg) {
+        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0);              // z = M r, rho = r.z, beta = 0
+        if (rc) return rc;
+        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.S);
+        DFDM_LAUNCH_OK("k_pcg_direction");
+    }
     int it = 0;
     while (it < maxiter) {
         int stop = std::min(maxiter, it + every);
@@ -824,10 +1201,17 @@ static int pcg_solve(const PlanDev& P, const LaneCfg& base, int B, PcgBuffers& w
             k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
             DFDM_LAUNCH_OK("k_pcg_spmv");
             prof_mark(st, 0, used);
-            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S, rtol * rtol);
+            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S,
+                                                                                    rtol * rtol, mg ? 1 : 0);
             DFDM_LAUNCH_OK("k_pcg_update");
             prof_mark(st, 1, used);
-            k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.p, w.S);
+            if (mg) {
+                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used);
+                if (rc) return rc;
+                prof_mark(st, -1, used);
+            }
+            k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r,
+                                                                                       mg ? w.mg.z[0] : nullptr, w.p, w.S);
             DFDM_LAUNCH_OK("k_pcg_direction");
             prof_mark(st, 2, used);
         }
@@ -864,7 +1248,10 @@ int run_pcg(Eval& ev) {
     if (cfg.nslabs > kMaxSlabs) cfg.nslabs = kMaxSlabs;
     Bump bump(ev.ws);
     PcgBuffers w{};
-    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w);
+    const bool use_mg = ev.M.n_levels > 0 && ev.opt.pcg_precond != DFDM_PRECOND_JACOBI;
+    int mn[kMaxMgLevels], mz[kMaxMgLevels];
+    for (int l = 0; l < ev.M.n_levels; ++l) { mn[l] = ev.M.lv[l].n; mz[l] = ev.M.lv[l].nnz; }
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, ev.M.n_levels, mn, mz);
     if (bump.off > ev.ws_bytes) {
         set_error("workspace too small for the PCG path: need " + std::to_string(bump.off) + " bytes");
         return DFDM_ENOMEM;
@@ -880,7 +1267,11 @@ int run_pcg(Eval& ev) {
     k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
     DFDM_LAUNCH_OK("k_assemble");
     g_iters[0] = g_iters[1] = 0;
-    rc = pcg_solve(P, cfg, B, w, ev.opt, st, host_flag, &g_iters[0]);
+    if (use_mg) {
+        rc = mg_setup(P, ev.M, cfg, B, w, st);
+        if (rc) return rc;
+    }
+    rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, st, host_flag, &g_iters[0]);
     if (rc) return rc;
     if (ev.status) {
         k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 0);
@@ -920,7 +1311,7 @@ int run_pcg(Eval& ev) {
     if (seeds) {
         k_adjoint_rhs<<<grid, kThreads, 0, st>>>(P, cfg, B, w.Xb, w.Ub, w.r);
         DFDM_LAUNCH_OK("k_adjoint_rhs");
-        rc = pcg_solve(P, cfg, B, w, ev.opt, st, host_flag, &g_iters[1]);
+        rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, st, host_flag, &g_iters[1]);
         if (rc) return rc;
         if (ev.status) {
             k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 1);

@@ -98,6 +98,147 @@ static int bandwidth(int nf, const std::vector<int32_t>& rowptr, const std::vect
     return w;
 }
 
+// ---- aggregation multigrid hierarchy (topology only) ----------------------------------------------
+// Pairwise matching applied twice per level (aggregates of up to 4 rows): visit rows by ascending
+// degree, match each unmatched row with its unmatched neighbour of largest connection weight
+// (weight = number of fine couplings the connection stands for).  Everything is integer and
+// deterministic; the numerical coarse operators are summed per design on the device.
+namespace {
+
+struct Graph {
+    int n = 0;
+    std::vector<int32_t> ptr, idx, wgt;   // adjacency without self loops
+};
+
+Graph graph_from_csr(int n, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx) {
+    Graph g;
+    g.n = n;
+    g.ptr.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            if (colidx[k] != i) {
+                g.idx.push_back(colidx[k]);
+                g.wgt.push_back(1);
+                g.ptr[i + 1]++;
+            }
+    for (int i = 0; i < n; ++i) g.ptr[i + 1] += g.ptr[i];
+    return g;
+}
+
+// one matching pass: returns the coarse graph and fills match[n] (coarse index of every node)
+Graph match_pass(const Graph& g, std::vector<int32_t>& match) {
+    const int n = g.n;
+    match.assign(n, -1);
+    std::vector<int32_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g.ptr[a + 1] - g.ptr[a] < g.ptr[b + 1] - g.ptr[b]; });
+    int nc = 0;
+    for (int i : order) {
+        if (match[i] >= 0) continue;
+        int best = -1, bw = -1;
+        for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+            int j = g.idx[k];
+            if (match[j] < 0 && j != i && g.wgt[k] > bw) {
+                bw = g.wgt[k];
+                best = j;
+            }
+        }
+        match[i] = nc;
+        if (best >= 0) match[best] = nc;
+        ++nc;
+    }
+    // coarse graph: sum the weights of parallel connections
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> rows(nc);
+    for (int i = 0; i < n; ++i)
+        for (int k = g.ptr[i]; k < g.ptr[i + 1]; ++k) {
+            int a = match[i], b = match[g.idx[k]];
+            if (a != b) rows[a].emplace_back(b, g.wgt[k]);
+        }
+    Graph c;
+    c.n = nc;
+    c.ptr.assign(nc + 1, 0);
+    for (int a = 0; a < nc; ++a) {
+        auto& r = rows[a];
+        std::sort(r.begin(), r.end());
+        for (size_t k = 0; k < r.size();) {
+            size_t e = k;
+            int w = 0;
+            while (e < r.size() && r[e].first == r[k].first) w += r[e++].second;
+            c.idx.push_back(r[k].first);
+            c.wgt.push_back(w);
+            k = e;
+        }
+        c.ptr[a + 1] = (int)c.idx.size();
+    }
+    return c;
+}
+
+}  // namespace
+
+static void build_multigrid(Plan& P) {
+    constexpr int kCoarsest = 24;
+    int n = P.nf;
+    std::vector<int32_t> rowptr = P.rowptr, colidx = P.colidx;
+    Graph g = graph_from_csr(n, rowptr, colidx);
+    while (n > kCoarsest && (int)P.mg.size() < kMaxMgLevels) {
+        std::vector<int32_t> m1, m2;
+        Graph g1 = match_pass(g, m1);
+        Graph g2 = match_pass(g1, m2);
+        if (g2.n >= n) break;                                  // no edges left to coarsen along
+        MgLevel L;
+        L.n_fine = n;
+        L.n = g2.n;
+        L.agg.resize(n);
+        for (int i = 0; i < n; ++i) L.agg[i] = m2[m1[i]];
+        L.mem_ptr.assign(L.n + 1, 0);
+        for (int i = 0; i < n; ++i) L.mem_ptr[L.agg[i] + 1]++;
+        for (int a = 0; a < L.n; ++a) L.mem_ptr[a + 1] += L.mem_ptr[a];
+        L.mem_idx.resize(n);
+        {
+            std::vector<int32_t> cur(L.mem_ptr.begin(), L.mem_ptr.end() - 1);
+            for (int i = 0; i < n; ++i) L.mem_idx[cur[L.agg[i]]++] = i;
+        }
+        // coarse pattern and the Galerkin gather lists from the fine pattern
+        const int nnz_f = rowptr[n];
+        std::vector<std::pair<int64_t, int32_t>> keyed(nnz_f);   // (coarse row * nc + coarse col, fine slot)
+        for (int i = 0; i < n; ++i)
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+                keyed[k] = {(int64_t)L.agg[i] * L.n + L.agg[colidx[k]], k};
+        std::sort(keyed.begin(), keyed.end());
+        L.rowptr.assign(L.n + 1, 0);
+        L.gal_ptr.push_back(0);
+        L.gal_src.resize(nnz_f);
+        L.diagslot.assign(L.n, -1);
+        for (int k = 0; k < nnz_f;) {
+            int e = k;
+            while (e < nnz_f && keyed[e].first == keyed[k].first) {
+                L.gal_src[e] = keyed[e].second;
+                ++e;
+            }
+            int row = (int)(keyed[k].first / L.n), col = (int)(keyed[k].first % L.n);
+            if (row == col) L.diagslot[row] = (int)L.colidx.size();
+            L.colidx.push_back(col);
+            L.rowptr[row + 1]++;
+            L.gal_ptr.push_back(e);
+            k = e;
+        }
+        for (int a = 0; a < L.n; ++a) L.rowptr[a + 1] += L.rowptr[a];
+        L.nnz = (int)L.colidx.size();
+        for (int a = 0; a < L.n; ++a) L.ell_w = std::max(L.ell_w, L.rowptr[a + 1] - L.rowptr[a]);
+        L.ell_col.assign((size_t)L.n * L.ell_w, 0);
+        for (int a = 0; a < L.n; ++a)
+            for (int u = 0; u < L.ell_w; ++u) {
+                int k = L.rowptr[a] + u;
+                L.ell_col[(size_t)a * L.ell_w + u] = k < L.rowptr[a + 1] ? L.colidx[k] : a;
+            }
+        rowptr = L.rowptr;
+        colidx = L.colidx;
+        n = L.n;
+        g = std::move(g2);
+        P.mg.push_back(std::move(L));
+    }
+}
+
 int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fixed, Plan& P) {
     if (n <= 0 || E < 0 || (E > 0 && !edges) || !is_fixed) {
         set_error("dfdm_plan_create: n must be positive and edges / is_fixed non-NULL");
@@ -197,6 +338,8 @@ int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fix
             P.ell_col[(size_t)f * P.ell_w + u] = real ? P.colidx[k] : f;
             P.ell_slot[(size_t)f * P.ell_w + u] = real ? k : -1;
         }
+
+    build_multigrid(P);
 
     // per-edge scatter slots (uu, vv, uv, vu)
     P.edge_slots.assign(4 * (size_t)E, -1);
@@ -310,6 +453,9 @@ int dfdm_plan_get_info(const dfdm_plan* plan, dfdm_plan_info* info) {
     info->direct_smem_bytes = dfdm::direct_smem_bytes(plan->nf, plan->w);
     info->direct_fits = info->direct_smem_bytes <= dfdm::kDirectSmemLimit ? 1 : 0;
     info->auto_solver = info->direct_fits ? DFDM_SOLVER_DIRECT : DFDM_SOLVER_PCG;
+    info->mg_levels = (int32_t)plan->mg.size();
+    info->mg_n_coarse = plan->mg.empty() ? 0 : plan->mg.front().n;
+    info->mg_n_coarsest = plan->mg.empty() ? 0 : plan->mg.back().n;
     return DFDM_OK;
 }
 

@@ -45,6 +45,32 @@ struct PlanDev {
     const int32_t* sinc_code = nullptr;
 };
 
+// One coarse level of the aggregation multigrid hierarchy (built from the level above it).
+// Coarse operator = Galerkin product with piecewise-constant prolongation: K_c(I,J) = sum of the
+// fine entries K(i,j), i in I, j in J - again a weighted graph Laplacian with grounding, so every
+// level has the same kernels.
+struct MgLevelDev {
+    int n_fine = 0, n = 0, nnz = 0, ell_w = 0;
+    const int32_t* agg = nullptr;        // [n_fine] fine row -> coarse row
+    const int32_t* mem_ptr = nullptr;    // [n+1]    coarse row -> its fine rows
+    const int32_t* mem_idx = nullptr;    // [n_fine]
+    const int32_t* rowptr = nullptr;     // [n+1]    coarse CSR (sorted columns)
+    const int32_t* ell_col = nullptr;    // [n][ell_w]
+    const int32_t* diagslot = nullptr;   // [n]
+    const int32_t* gal_ptr = nullptr;    // [nnz+1]  coarse slot -> fine slots (Galerkin sum)
+    const int32_t* gal_src = nullptr;    // [nnz_fine]
+};
+constexpr int kMaxMgLevels = 12;
+struct MgDev {
+    int n_levels = 0;                    // number of COARSE levels
+    MgLevelDev lv[kMaxMgLevels];
+};
+
+struct MgLevel {
+    int n_fine = 0, n = 0, nnz = 0, ell_w = 0;
+    std::vector<int32_t> agg, mem_ptr, mem_idx, rowptr, colidx, ell_col, diagslot, gal_ptr, gal_src;
+};
+
 struct Plan {
     int n = 0, E = 0, nf = 0, nx = 0, nnz = 0, w_nat = 0, w = 0;
     bool use_rcm = false;
@@ -56,6 +82,8 @@ struct Plan {
     std::vector<int32_t> ninc_ptr, ninc_edge, ninc_sign;
     std::vector<int32_t> perm, pos;
     std::vector<int32_t> sinc_ptr, sinc_edge, sinc_code;
+    std::vector<MgLevel> mg;              // coarse levels, finest first
+    mutable std::map<int, MgDev> mg_dev;
 
     // lazily created device mirrors and cached arenas for the *_host entry points
     mutable std::mutex mu;

@@ -61,9 +61,14 @@ typedef struct dfdm_options {
     int32_t solver;          /* DFDM_SOLVER_*; AUTO picks DIRECT when the band fits shared memory */
     int32_t pcg_maxiter;     /* <= 0: default 20 * sqrt(n_free) + 2000 */
     double pcg_rtol;         /* <= 0: default 1e-12 on ||r|| / ||b|| per design and coordinate */
-    int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 */
-    int32_t reserved;
+    int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 (Jacobi) / 5 (multigrid) */
+    int32_t pcg_precond;     /* DFDM_PRECOND_*; AUTO = aggregation multigrid V-cycle when the plan has coarse levels */
 } dfdm_options;
+
+/* preconditioner of the PCG path */
+#define DFDM_PRECOND_AUTO 0
+#define DFDM_PRECOND_JACOBI 1      /* z = r / diag(K) */
+#define DFDM_PRECOND_MULTIGRID 2   /* one V(1,1) cycle of plain-aggregation multigrid, damped-Jacobi smoothing */
 
 typedef struct dfdm_plan_info {
     int32_t n, n_edges, n_free, n_fixed;
@@ -73,7 +78,9 @@ typedef struct dfdm_plan_info {
     int32_t direct_fits;         /* 1 if the banded factor + 3 right-hand sides fit one CTA's shared memory */
     int64_t direct_smem_bytes;
     int32_t auto_solver;         /* what DFDM_SOLVER_AUTO resolves to */
-    int32_t reserved;
+    int32_t mg_levels;           /* coarse levels of the aggregation multigrid hierarchy (0: Jacobi only) */
+    int32_t mg_n_coarse;         /* rows of the first coarse level */
+    int32_t mg_n_coarsest;       /* rows of the last coarse level */
 } dfdm_plan_info;
 
 /* index arrays exposed for bit-exact parity tests (host pointers owned by the plan) */
@@ -198,13 +205,16 @@ DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_
 /*
  * Per-kernel timing of the PCG loop for roofline accounting: when enabled, a CUDA event is recorded on
  * the launch stream after every PCG kernel and resolved at the convergence polls.
- * ms / count are indexed by DFDM_PROF_* (4 entries each).  Not thread safe; meant for bench.py.
+ * ms / count are indexed by DFDM_PROF_* (8 entries each).  Not thread safe; meant for bench.py.
  */
 #define DFDM_PROF_SPMV 0       /* k_pcg_spmv:      Ap = K p, p.Ap            algorithmic bytes 8 nnz + 48 n_free per design */
 #define DFDM_PROF_UPDATE 1     /* k_pcg_update:    x, r update, r.z, r.r     152 n_free per design */
 #define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: p = z + beta p            80 n_free per design */
+#define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   8 nnz + 48 n_free + 24 n_coarse */
+#define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          8 nnz + 80 n_free + 24 n_coarse */
+#define DFDM_PROF_MG_COARSE 5  /* all kernels below the finest level, per V-cycle */
 DFDM_API void dfdm_profile_enable(int32_t on);
-DFDM_API void dfdm_profile_read(double* ms /* [4] */, int64_t* count /* [4] */);
+DFDM_API void dfdm_profile_read(double* ms /* [8] */, int64_t* count /* [8] */);
 
 #ifdef __cplusplus
 }
