@@ -230,7 +230,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond)
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over)
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -385,6 +385,8 @@ def main():
     ap.add_argument("--pcg-check-every", type=int, default=0)
     ap.add_argument("--pcg-maxiter", type=int, default=0, help="cap PCG iterations (kernel tuning runs only: results not converged)")
     ap.add_argument("--precond", default="auto", choices=["auto", "jacobi", "multigrid"])
+    ap.add_argument("--mg-omega", type=float, default=0.0)
+    ap.add_argument("--mg-over", type=float, default=0.0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

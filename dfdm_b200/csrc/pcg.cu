@@ -457,8 +457,9 @@ struct MgMat {                 // one level's operator (level 0: the plan's CSR)
     const double* dinv;        // 1 / diag   [n][B]
 };
 
-constexpr double kMgOmega = 0.8;
-constexpr double kMgOver = 1.5;
+constexpr double kMgOmegaDefault = 0.8;
+constexpr double kMgOverDefault = 1.7;
+struct MgParams { double omega, over; };
 
 // coarse operator values: sum of the fine values feeding each coarse slot, then 1 / diagonal
 __global__ void __launch_bounds__(kThreads) k_mg_galerkin(MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ vals_f,
@@ -522,7 +523,8 @@ __device__ __forceinline__ void mg_row(const int32_t* __restrict__ ell_col, int 
 // One thread per (coarse row, design): it owns the aggregate, so the restriction needs no atomics.
 __global__ void __launch_bounds__(kThreads, 3) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
                                                         double* __restrict__ t, double* __restrict__ b_coarse,
-                                                        const int32_t* __restrict__ n_active) {
+                                                        const int32_t* __restrict__ n_active, MgParams mp) {
+    const double kMgOmega = mp.omega;
     if (__ldcg(&n_active[1]) == 0) return;
     LANE_SETUP();
     if (!live) return;
@@ -550,7 +552,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_mg_down(MgMat A, MgLevelDev L, 
 // up pass of level l: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
 __global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
                                                       const double* __restrict__ t, const double* __restrict__ e_coarse,
-                                                      double* __restrict__ z, PcgScalars S, int dots, int first) {
+                                                      double* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
+    const double kMgOmega = mp.omega, kMgOver = mp.over;
     if (__ldcg(&S.n_active[1]) == 0) return;
     LANE_SETUP();
     double v[3] = {0, 0, 0};
@@ -637,31 +640,44 @@ __global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, 
     }
 }
 
-// coarsest solve: e = K_c^-1 b for the three coordinates; one thread per (coordinate, design)
-__global__ void k_mg_coarsest_solve(int n, int B, const double* __restrict__ Lf, const double* __restrict__ bvec, double* __restrict__ e,
-                                    const int32_t* __restrict__ n_active) {
+// explicit inverse of the coarsest operator from its LDL^T: one thread per (column, design) solves for a unit vector.
+// The V-cycle then applies it as a dense product, which is parallel over rows instead of a serial substitution.
+__global__ void k_mg_coarsest_inverse(int n, int B, const double* __restrict__ Lf, double* __restrict__ inv) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * B) return;
+    int col = idx / B, b = idx - col * B;
+    const size_t sB = (size_t)B;
+    double* x = inv + (size_t)col * n * sB + b;          // column `col`, entries at stride B
+    for (int i = 0; i < n; ++i) {
+        double yi = i == col ? 1.0 : 0.0;
+        for (int j = 0; j < i; ++j) yi -= Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * x[(size_t)j * sB];
+        x[(size_t)i * sB] = yi;
+    }
+    for (int i = 0; i < n; ++i) x[(size_t)i * sB] /= Lf[(size_t)(i * (i + 1) / 2 + i) * sB + b];
+    for (int i = n - 1; i >= 0; --i) {
+        double xi = x[(size_t)i * sB];
+        for (int j = i + 1; j < n; ++j) xi -= Lf[(size_t)(j * (j + 1) / 2 + i) * sB + b] * x[(size_t)j * sB];
+        x[(size_t)i * sB] = xi;
+    }
+}
+
+// coarsest solve: e = K_c^-1 b as a dense product; one thread per (row, coordinate, design)
+__global__ void k_mg_coarsest_solve(int n, int B, const double* __restrict__ inv, const double* __restrict__ bvec,
+                                    double* __restrict__ e, const int32_t* __restrict__ n_active) {
     if (__ldcg(&n_active[1]) == 0) return;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 3 * B) return;
-    int c = idx / B, b = idx - c * B;
+    if (idx >= n * 3 * B) return;
+    int b = idx % B, rc = idx / B, c = rc % 3, i = rc / 3;
     const size_t sB = (size_t)B;
-    // forward: L y = b (y stored in e)
-    for (int i = 0; i < n; ++i) {
-        double yi = bvec[((size_t)i * 3 + c) * sB + b];
-        for (int j = 0; j < i; ++j) yi -= Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * e[((size_t)j * 3 + c) * sB + b];
-        e[((size_t)i * 3 + c) * sB + b] = yi;
-    }
-    for (int i = 0; i < n; ++i) e[((size_t)i * 3 + c) * sB + b] /= Lf[(size_t)(i * (i + 1) / 2 + i) * sB + b];
-    for (int i = n - 1; i >= 0; --i) {
-        double xi = e[((size_t)i * 3 + c) * sB + b];
-        for (int j = i + 1; j < n; ++j) xi -= Lf[(size_t)(j * (j + 1) / 2 + i) * sB + b] * e[((size_t)j * 3 + c) * sB + b];
-        e[((size_t)i * 3 + c) * sB + b] = xi;
-    }
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];   // symmetric: column j, row i
+    e[((size_t)i * 3 + c) * sB + b] = acc;
 }
 
 // coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
 __global__ void k_mg_coarsest_jacobi(MgMat A, int B, int sweeps, const double* __restrict__ bvec, double* __restrict__ e,
-                                     double* __restrict__ tmp, const int32_t* __restrict__ n_active) {
+                                     double* __restrict__ tmp, const int32_t* __restrict__ n_active, MgParams mp) {
+    const double kMgOmega = mp.omega;
     if (__ldcg(&n_active[1]) == 0) return;
     // one CTA per design (all rows, three coordinates): rows in a loop, sweeps separated by block barriers
     int b = blockIdx.x;
@@ -973,6 +989,7 @@ struct MgBuffers {
     double* t[kMaxMgLevels + 1] = {nullptr};
     double* z[kMaxMgLevels + 1] = {nullptr};
     double* Lf = nullptr;
+    double* inv = nullptr;
     double* tmp = nullptr;
 };
 
@@ -1002,7 +1019,10 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
             w.mg.z[l] = bump.take<double>(nl * 3 * B);
         }
         int64_t nc = mg_n[mg_levels - 1];
-        if (nc <= kCoarsestDense) w.mg.Lf = bump.take<double>(nc * (nc + 1) / 2 * B);
+        if (nc <= kCoarsestDense) {
+            w.mg.Lf = bump.take<double>(nc * (nc + 1) / 2 * B);
+            w.mg.inv = bump.take<double>(nc * nc * B);
+        }
         else w.mg.tmp = bump.take<double>(nc * 3 * B);
     }
     w.qT = bump.take<double>(E * B);
@@ -1132,30 +1152,32 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
     if (w.mg.Lf) {
         k_mg_coarsest_factor<<<(B + 63) / 64, 64, 0, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.Lf);
         DFDM_LAUNCH_OK("k_mg_coarsest_factor");
+        k_mg_coarsest_inverse<<<(C.n * B + 127) / 128, 128, 0, st>>>(C.n, B, w.mg.Lf, w.mg.inv);
+        DFDM_LAUNCH_OK("k_mg_coarsest_inverse");
     }
     return DFDM_OK;
 }
 
 // z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
 static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
-                     size_t& used) {
+                     size_t& used, MgParams mp) {
     const int nl = M.n_levels;
     w.mg.b[0] = w.r;
     w.mg.t[0] = w.Ap;           // Ap is dead between the update and the next SpMV
     for (int l = 0; l < nl; ++l) {
         MgMat A = mg_mat(P, M, w, l);
         LaneCfg c = rows_cfg(k_mg_down, base, M.lv[l].n);
-        k_mg_down<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active);
+        k_mg_down<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
         DFDM_LAUNCH_OK("k_mg_down");
         if (l == 0) prof_mark(st, 3, used);
     }
     const MgLevelDev& C = M.lv[nl - 1];
     if (w.mg.Lf) {
-        k_mg_coarsest_solve<<<(3 * B + 63) / 64, 64, 0, st>>>(C.n, B, w.mg.Lf, w.mg.b[nl], w.mg.z[nl], w.S.n_active);
+        k_mg_coarsest_solve<<<(C.n * 3 * B + 255) / 256, 256, 0, st>>>(C.n, B, w.mg.inv, w.mg.b[nl], w.mg.z[nl], w.S.n_active);
         DFDM_LAUNCH_OK("k_mg_coarsest_solve");
     } else {
         MgMat A = mg_mat(P, M, w, nl);
-        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active);
+        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active, mp);
         DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
     }
     for (int l = nl - 1; l >= 0; --l) {
@@ -1163,7 +1185,7 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
         LaneCfg c = rows_cfg(k_mg_up, base, A.n);
         if (l == 0) prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
         k_mg_up<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
-                                                          l == 0 ? 1 : 0, first);
+                                                          l == 0 ? 1 : 0, first, mp);
         DFDM_LAUNCH_OK("k_mg_up");
         if (l == 0) prof_mark(st, 4, used);
     }
@@ -1173,6 +1195,7 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
 static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
                      cudaStream_t st, int32_t* host_flag, int* iters_out) {
     const bool mg = M != nullptr && M->n_levels > 0;
+    MgParams mp{opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault, opt.mg_over > 0 ? opt.mg_over : kMgOverDefault};
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
     const LaneCfg cfg_spmv = one_wave(k_pcg_spmv, base, P.nf, kThreads);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
@@ -1187,7 +1210,7 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used0 = 0;
     if (mg) {
-        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0);              // z = M r, rho = r.z, beta = 0
+        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0, mp);              // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
         k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.S);
         DFDM_LAUNCH_OK("k_pcg_direction");
@@ -1206,7 +1229,7 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
             DFDM_LAUNCH_OK("k_pcg_update");
             prof_mark(st, 1, used);
             if (mg) {
-                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used);
+                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used, mp);
                 if (rc) return rc;
                 prof_mark(st, -1, used);
             }

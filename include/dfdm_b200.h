@@ -63,6 +63,8 @@ typedef struct dfdm_options {
     double pcg_rtol;         /* <= 0: default 1e-12 on ||r|| / ||b|| per design and coordinate */
     int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 (Jacobi) / 5 (multigrid) */
     int32_t pcg_precond;     /* DFDM_PRECOND_*; AUTO = aggregation multigrid V-cycle when the plan has coarse levels */
+    double mg_omega;         /* damping of the Jacobi smoother; <= 0: default 0.8 */
+    double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects); <= 0: default 1.5 */
 } dfdm_options;
 
 /* preconditioner of the PCG path */
