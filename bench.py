@@ -329,9 +329,11 @@ def gpu_arm(args, rank, world, local_rank):
             "gpu_launches": launches}
     if solver == "pcg" and sum(prof_count) > 0:
         nc = plan.info.get("mg_n_coarse", 0)
-        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": 80.0 * nf * batch,
-               "k_mg_down[level 0]": (8.0 * nnz + 48.0 * nf + 24.0 * nc) * batch,
-               "k_mg_up[level 0]": (8.0 * nnz + 80.0 * nf + 24.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
+        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": (68.0 if plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi" else 80.0) * nf * batch,
+               # single-precision V-cycle: K D^-1 (4 nnz), r in double (24 nf), t out (12 nf), coarse rhs out (12 nc)
+               "k_mg_down[level 0]": (4.0 * nnz + 36.0 * nf + 12.0 * nc) * batch,
+               # K (4 nnz), r (24 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
+               "k_mg_up[level 0]": (4.0 * nnz + 52.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
         kernels = []
         for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction", "k_mg_down[level 0]", "k_mg_up[level 0]",
                                   "multigrid coarse levels (per V-cycle)")):

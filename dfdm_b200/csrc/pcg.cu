@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
 
 // p = r / diag + beta p
 __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                              const double* __restrict__ r, const double* __restrict__ z,
+                                                              const double* __restrict__ r, const float* __restrict__ z,
                                                               double* __restrict__ p, PcgScalars S) {
     if (__ldcg(&S.n_active[1]) == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1] = __ldcg(&S.n_active[0]);   // p is dead once everything converged
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg c
 #pragma unroll 2
     for (int f = row0; f < nf; f += rstride) {
         size_t o = ((size_t)f * 3 + c) * B + b;
-        double zc = z ? z[o] : r[o] * dinv[(size_t)f * B + b];
+        double zc = z ? (double)z[o] : r[o] * dinv[(size_t)f * B + b];
         p[o] = zc + be * p[o];
     }
 }
@@ -448,42 +448,65 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg c
 // correction is scaled by a constant, so M is symmetric positive definite whenever K is definite.
 // ------------------------------------------------------------------------------------------------
 
-struct MgMat {                 // one level's operator (level 0: the plan's CSR)
+// The whole V-cycle works on single-precision copies: a preconditioner needs a few digits, and the
+// outer CG keeps its residual recurrence in double precision, so halving the bytes of every V-cycle
+// pass costs no accuracy in the solution.
+typedef float mgf;
+
+struct MgMat {                 // one level's operator (level 0: the plan's CSR pattern)
     int n, ell_w;
     const int32_t* rowptr;
     const int32_t* ell_col;
-    const double* vals;        // K          [nnz][B]
-    const double* vals_s;      // K D^-1     [nnz][B]
-    const double* dinv;        // 1 / diag   [n][B]
+    const mgf* vals;           // K          [nnz][B]
+    const mgf* vals_s;         // K D^-1     [nnz][B]
+    const mgf* dinv;           // 1 / diag   [n][B]
 };
 
 constexpr double kMgOmegaDefault = 0.8;
 constexpr double kMgOverDefault = 1.7;
-struct MgParams { double omega, over; };
+struct MgParams { float omega, over; };
 
-// coarse operator values: sum of the fine values feeding each coarse slot, then 1 / diagonal
-__global__ void __launch_bounds__(kThreads) k_mg_galerkin(MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ vals_f,
-                                                         double* __restrict__ vals_c) {
+// level 0: single-precision copies of K, K D^-1 and 1/diag from the assembled double-precision operator
+__global__ void __launch_bounds__(kThreads) k_mg_prepare0(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col,
+                                                         int W, LaneCfg cfg, int B, const double* __restrict__ vals,
+                                                         const double* __restrict__ dinv, mgf* __restrict__ vals32,
+                                                         mgf* __restrict__ vals_s32, mgf* __restrict__ dinv32) {
+    LANE_SETUP();
+    if (!live) return;
+    for (int f = row0; f < n; f += rstride) {
+        int k0 = rowptr[f], len = rowptr[f + 1] - k0;
+        for (int u = 0; u < len; ++u) {
+            double a = vals[(size_t)(k0 + u) * B + b];
+            vals32[(size_t)(k0 + u) * B + b] = (mgf)a;
+            vals_s32[(size_t)(k0 + u) * B + b] = (mgf)(a * dinv[(size_t)ell_col[(size_t)f * W + u] * B + b]);
+        }
+        dinv32[(size_t)f * B + b] = (mgf)dinv[(size_t)f * B + b];
+    }
+}
+
+// coarse operator values: sum of the fine values feeding each coarse slot
+__global__ void __launch_bounds__(kThreads) k_mg_galerkin(MgLevelDev L, LaneCfg cfg, int B, const mgf* __restrict__ vals_f,
+                                                         mgf* __restrict__ vals_c) {
     LANE_SETUP();
     if (!live) return;
     for (int s = row0; s < L.nnz; s += rstride) {
         double acc = 0.0;
-        for (int k = L.gal_ptr[s]; k < L.gal_ptr[s + 1]; ++k) acc += vals_f[(size_t)L.gal_src[k] * B + b];
-        vals_c[(size_t)s * B + b] = acc;
+        for (int k = L.gal_ptr[s]; k < L.gal_ptr[s + 1]; ++k) acc += (double)vals_f[(size_t)L.gal_src[k] * B + b];
+        vals_c[(size_t)s * B + b] = (mgf)acc;
     }
 }
 
+// coarse level: 1/diag and the column-scaled copy K D^-1
 __global__ void __launch_bounds__(kThreads) k_mg_dinv(int n, const int32_t* __restrict__ diagslot, LaneCfg cfg, int B,
-                                                     const double* __restrict__ vals, double* __restrict__ dinv) {
+                                                     const mgf* __restrict__ vals, mgf* __restrict__ dinv) {
     LANE_SETUP();
     if (!live) return;
-    for (int f = row0; f < n; f += rstride) dinv[(size_t)f * B + b] = 1.0 / vals[(size_t)diagslot[f] * B + b];
+    for (int f = row0; f < n; f += rstride) dinv[(size_t)f * B + b] = 1.0f / vals[(size_t)diagslot[f] * B + b];
 }
 
-// vals_s[k] = vals[k] * dinv[col(k)]
 __global__ void __launch_bounds__(kThreads) k_mg_scale(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col,
-                                                      int W, LaneCfg cfg, int B, const double* __restrict__ vals,
-                                                      const double* __restrict__ dinv, double* __restrict__ vals_s) {
+                                                      int W, LaneCfg cfg, int B, const mgf* __restrict__ vals,
+                                                      const mgf* __restrict__ dinv, mgf* __restrict__ vals_s) {
     LANE_SETUP();
     if (!live) return;
     for (int f = row0; f < n; f += rstride) {
@@ -493,54 +516,57 @@ __global__ void __launch_bounds__(kThreads) k_mg_scale(int n, const int32_t* __r
     }
 }
 
-// row product helper: acc[c] = sum_u val[k0+u] * vec[col(u)][c]
-__device__ __forceinline__ void mg_row(const int32_t* __restrict__ ell_col, int W, int f, int k0, int len, const double* __restrict__ vb,
-                                       const double* __restrict__ xb, size_t sB, double acc[3]) {
+// row product helper: acc[c] += sum_u val[k0+u] * vec[col(u)][c]; all loads of a batch issued before use
+template <typename TV>
+__device__ __forceinline__ void mg_row(const int32_t* __restrict__ ell_col, int W, int f, int k0, int len, const mgf* __restrict__ vb,
+                                       const TV* __restrict__ xb, size_t sB, float acc[3]) {
     constexpr int U = 5;
     for (int u0 = 0; u0 < len; u0 += U) {
         int col[U];
-        double a[U], x0[U], x1[U], x2[U];
+        float a[U];
+        TV x0[U], x1[U], x2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) col[u] = ell_col[(size_t)f * W + min(u0 + u, len - 1)];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            a[u] = u0 + u < len ? vb[(size_t)(k0 + u0 + u) * sB] : 0.0;
-            const double* xj = xb + (size_t)col[u] * 3 * sB;
+            a[u] = u0 + u < len ? vb[(size_t)(k0 + u0 + u) * sB] : 0.0f;
+            const TV* xj = xb + (size_t)col[u] * 3 * sB;
             x0[u] = xj[0];
             x1[u] = xj[sB];
             x2[u] = xj[2 * sB];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            acc[0] += a[u] * x0[u];
-            acc[1] += a[u] * x1[u];
-            acc[2] += a[u] * x2[u];
+            acc[0] += a[u] * (float)x0[u];
+            acc[1] += a[u] * (float)x1[u];
+            acc[2] += a[u] * (float)x2[u];
         }
     }
 }
 
-// down pass of level l (operator A, right-hand side bvec): writes t = (K D^-1) b and the coarse right-hand side.
-// One thread per (coarse row, design): it owns the aggregate, so the restriction needs no atomics.
-__global__ void __launch_bounds__(kThreads, 3) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
-                                                        double* __restrict__ t, double* __restrict__ b_coarse,
+// down pass of a level (operator A, right-hand side bvec of type TB: the double-precision CG residual on level 0,
+// single precision below): writes t = (K D^-1) b and the coarse right-hand side.  One thread per (coarse row,
+// design): it owns the aggregate, so the restriction needs no atomics.
+template <typename TB>
+__global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
+                                                        mgf* __restrict__ t, mgf* __restrict__ b_coarse,
                                                         const int32_t* __restrict__ n_active, MgParams mp) {
-    const double kMgOmega = mp.omega;
     if (__ldcg(&n_active[1]) == 0) return;
     LANE_SETUP();
     if (!live) return;
     const size_t sB = (size_t)B;
     for (int I = row0; I < L.n; I += rstride) {
-        double rc[3] = {0.0, 0.0, 0.0};
+        float rc[3] = {0.0f, 0.0f, 0.0f};
         for (int m = L.mem_ptr[I]; m < L.mem_ptr[I + 1]; ++m) {
             int f = L.mem_idx[m];
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
-            double acc[3] = {0.0, 0.0, 0.0};
-            mg_row(A.ell_col, A.ell_w, f, k0, len, A.vals_s + b, bvec + b, sB, acc);
+            float acc[3] = {0.0f, 0.0f, 0.0f};
+            mg_row<TB>(A.ell_col, A.ell_w, f, k0, len, A.vals_s + b, bvec + b, sB, acc);
             size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 t[o + c * sB] = acc[c];
-                rc[c] += bvec[o + c * sB] - kMgOmega * acc[c];
+                rc[c] += (float)bvec[o + c * sB] - mp.omega * acc[c];
             }
         }
         size_t oc = (size_t)I * 3 * sB + b;
@@ -549,11 +575,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_mg_down(MgMat A, MgLevelDev L, 
     }
 }
 
-// up pass of level l: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
-__global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const double* __restrict__ bvec,
-                                                      const double* __restrict__ t, const double* __restrict__ e_coarse,
-                                                      double* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
-    const double kMgOmega = mp.omega, kMgOver = mp.over;
+// up pass of a level: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
+template <typename TB>
+__global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
+                                                      const mgf* __restrict__ t, const mgf* __restrict__ e_coarse,
+                                                      mgf* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
     if (__ldcg(&S.n_active[1]) == 0) return;
     LANE_SETUP();
     double v[3] = {0, 0, 0};
@@ -562,17 +588,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, La
         for (int f = row0; f < A.n; f += rstride) {
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
             // s = (K P e)_f: gather the coarse solution through the aggregate map
-            double sacc[3] = {0.0, 0.0, 0.0};
+            float sacc[3] = {0.0f, 0.0f, 0.0f};
             constexpr int U = 5;
             for (int u0 = 0; u0 < len; u0 += U) {
                 int cg[U];
-                double a[U], x0[U], x1[U], x2[U];
+                float a[U], x0[U], x1[U], x2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) cg[u] = L.agg[A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)]];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    a[u] = u0 + u < len ? A.vals[(size_t)(k0 + u0 + u) * sB + b] : 0.0;
-                    const double* ej = e_coarse + (size_t)cg[u] * 3 * sB + b;
+                    a[u] = u0 + u < len ? A.vals[(size_t)(k0 + u0 + u) * sB + b] : 0.0f;
+                    const mgf* ej = e_coarse + (size_t)cg[u] * 3 * sB + b;
                     x0[u] = ej[0];
                     x1[u] = ej[sB];
                     x2[u] = ej[2 * sB];
@@ -584,16 +610,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, La
                     sacc[2] += a[u] * x2[u];
                 }
             }
-            const double wd = kMgOmega * A.dinv[(size_t)f * sB + b];
-            const double* ei = e_coarse + (size_t)L.agg[f] * 3 * sB + b;
+            const float wd = mp.omega * A.dinv[(size_t)f * sB + b];
+            const mgf* ei = e_coarse + (size_t)L.agg[f] * 3 * sB + b;
             size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                double bc = bvec[o + c * sB];
-                double xn = wd * bc + kMgOver * ei[c * sB];
-                double zc = xn + wd * (bc - kMgOmega * t[o + c * sB] - kMgOver * sacc[c]);
+                TB bfull = bvec[o + c * sB];
+                float bc = (float)bfull;
+                float xn = wd * bc + mp.over * ei[c * sB];
+                float zc = xn + wd * (bc - mp.omega * t[o + c * sB] - mp.over * sacc[c]);
                 z[o + c * sB] = zc;
-                v[c] += bc * zc;
+                v[c] += (double)bfull * (double)zc;
             }
         }
     }
@@ -613,9 +640,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_mg_up(MgMat A, MgLevelDev L, La
     }
 }
 
-// coarsest level: dense LDL^T per design, interleaved storage Lf[(i(i+1)/2 + j)][B]; one thread per design
+// coarsest level: dense LDL^T per design in double precision, interleaved storage Lf[(i(i+1)/2 + j)][B]
 __global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col, int W, int B,
-                                     const double* __restrict__ vals, double* __restrict__ Lf) {
+                                     const mgf* __restrict__ vals, double* __restrict__ Lf) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const size_t sB = (size_t)B;
@@ -625,7 +652,7 @@ __global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, 
         int k0 = rowptr[i], len = rowptr[i + 1] - k0;
         for (int u = 0; u < len; ++u) {
             int j = ell_col[(size_t)i * W + u];
-            if (j <= i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = vals[(size_t)(k0 + u) * sB + b];
+            if (j <= i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = (double)vals[(size_t)(k0 + u) * sB + b];
         }
     }
     // right-looking LDL^T in place: strictly lower part ends up holding L, the diagonal D
@@ -642,12 +669,12 @@ __global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, 
 
 // explicit inverse of the coarsest operator from its LDL^T: one thread per (column, design) solves for a unit vector.
 // The V-cycle then applies it as a dense product, which is parallel over rows instead of a serial substitution.
-__global__ void k_mg_coarsest_inverse(int n, int B, const double* __restrict__ Lf, double* __restrict__ inv) {
+__global__ void k_mg_coarsest_inverse(int n, int B, const double* __restrict__ Lf, double* __restrict__ work, mgf* __restrict__ inv) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * B) return;
     int col = idx / B, b = idx - col * B;
     const size_t sB = (size_t)B;
-    double* x = inv + (size_t)col * n * sB + b;          // column `col`, entries at stride B
+    double* x = work + (size_t)col * n * sB + b;          // column `col`, entries at stride B
     for (int i = 0; i < n; ++i) {
         double yi = i == col ? 1.0 : 0.0;
         for (int j = 0; j < i; ++j) yi -= Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * x[(size_t)j * sB];
@@ -659,45 +686,45 @@ __global__ void k_mg_coarsest_inverse(int n, int B, const double* __restrict__ L
         for (int j = i + 1; j < n; ++j) xi -= Lf[(size_t)(j * (j + 1) / 2 + i) * sB + b] * x[(size_t)j * sB];
         x[(size_t)i * sB] = xi;
     }
+    for (int i = 0; i < n; ++i) inv[((size_t)col * n + i) * sB + b] = (mgf)x[(size_t)i * sB];
 }
 
 // coarsest solve: e = K_c^-1 b as a dense product; one thread per (row, coordinate, design)
-__global__ void k_mg_coarsest_solve(int n, int B, const double* __restrict__ inv, const double* __restrict__ bvec,
-                                    double* __restrict__ e, const int32_t* __restrict__ n_active) {
+__global__ void k_mg_coarsest_solve(int n, int B, const mgf* __restrict__ inv, const mgf* __restrict__ bvec, mgf* __restrict__ e,
+                                    const int32_t* __restrict__ n_active) {
     if (__ldcg(&n_active[1]) == 0) return;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * 3 * B) return;
     int b = idx % B, rc = idx / B, c = rc % 3, i = rc / 3;
     const size_t sB = (size_t)B;
-    double acc = 0.0;
+    float acc = 0.0f;
     for (int j = 0; j < n; ++j) acc += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];   // symmetric: column j, row i
     e[((size_t)i * 3 + c) * sB + b] = acc;
 }
 
 // coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
-__global__ void k_mg_coarsest_jacobi(MgMat A, int B, int sweeps, const double* __restrict__ bvec, double* __restrict__ e,
-                                     double* __restrict__ tmp, const int32_t* __restrict__ n_active, MgParams mp) {
-    const double kMgOmega = mp.omega;
+__global__ void k_mg_coarsest_jacobi(MgMat A, int B, int sweeps, const mgf* __restrict__ bvec, mgf* __restrict__ e,
+                                     mgf* __restrict__ tmp, const int32_t* __restrict__ n_active, MgParams mp) {
     if (__ldcg(&n_active[1]) == 0) return;
     // one CTA per design (all rows, three coordinates): rows in a loop, sweeps separated by block barriers
     int b = blockIdx.x;
     if (b >= B) return;
     const size_t sB = (size_t)B;
-    for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) e[(size_t)i * sB + b] = kMgOmega * A.dinv[(size_t)(i / 3) * sB + b] * bvec[(size_t)i * sB + b];
+    for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) e[(size_t)i * sB + b] = mp.omega * A.dinv[(size_t)(i / 3) * sB + b] * bvec[(size_t)i * sB + b];
     __syncthreads();
-    double* src = e;
-    double* dst = tmp;
+    mgf* src = e;
+    mgf* dst = tmp;
     for (int s = 0; s < sweeps; ++s) {
         for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) {
             int f = i / 3, c = i - f * 3;
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
-            double acc = 0.0;
+            float acc = 0.0f;
             for (int u = 0; u < len; ++u)
                 acc += A.vals[(size_t)(k0 + u) * sB + b] * src[((size_t)A.ell_col[(size_t)f * A.ell_w + u] * 3 + c) * sB + b];
-            dst[(size_t)i * sB + b] = src[(size_t)i * sB + b] + kMgOmega * A.dinv[(size_t)f * sB + b] * (bvec[(size_t)i * sB + b] - acc);
+            dst[(size_t)i * sB + b] = src[(size_t)i * sB + b] + mp.omega * A.dinv[(size_t)f * sB + b] * (bvec[(size_t)i * sB + b] - acc);
         }
         __syncthreads();
-        double* sw = src; src = dst; dst = sw;
+        mgf* sw = src; src = dst; dst = sw;
     }
     if (src != e)
         for (int i = threadIdx.x; i < A.n * 3; i += blockDim.x) e[(size_t)i * sB + b] = src[(size_t)i * sB + b];
@@ -982,15 +1009,16 @@ constexpr int kCoarsestDense = 48;     // dense LDL^T on the coarsest level up t
 
 struct MgBuffers {
     int n_levels = 0;                                  // coarse levels in use
-    double* vals[kMaxMgLevels + 1] = {nullptr};
-    double* vals_s[kMaxMgLevels + 1] = {nullptr};
-    double* dinv[kMaxMgLevels + 1] = {nullptr};
-    double* b[kMaxMgLevels + 1] = {nullptr};
-    double* t[kMaxMgLevels + 1] = {nullptr};
-    double* z[kMaxMgLevels + 1] = {nullptr};
+    mgf* vals[kMaxMgLevels + 1] = {nullptr};
+    mgf* vals_s[kMaxMgLevels + 1] = {nullptr};
+    mgf* dinv[kMaxMgLevels + 1] = {nullptr};
+    mgf* b[kMaxMgLevels + 1] = {nullptr};              // level 0: the CG residual itself (double), not stored here
+    mgf* t[kMaxMgLevels + 1] = {nullptr};
+    mgf* z[kMaxMgLevels + 1] = {nullptr};
     double* Lf = nullptr;
-    double* inv = nullptr;
-    double* tmp = nullptr;
+    double* inv_work = nullptr;
+    mgf* inv = nullptr;
+    mgf* tmp = nullptr;
 };
 
 struct PcgBuffers {
@@ -1007,23 +1035,27 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
                   int nchunks_max, PcgBuffers& w, int mg_levels, const int* mg_n, const int* mg_nnz) {
     w.mg.n_levels = mg_levels;
     if (mg_levels > 0) {
-        w.mg.vals_s[0] = bump.take<double>(nnz * B);
-        w.mg.z[0] = bump.take<double>(nf * 3 * B);
+        w.mg.vals[0] = bump.take<mgf>(nnz * B);
+        w.mg.vals_s[0] = bump.take<mgf>(nnz * B);
+        w.mg.dinv[0] = bump.take<mgf>(nf * B);
+        w.mg.z[0] = bump.take<mgf>(nf * 3 * B);
         for (int l = 1; l <= mg_levels; ++l) {
             int64_t nl = mg_n[l - 1], zl = mg_nnz[l - 1];
-            w.mg.vals[l] = bump.take<double>(zl * B);
-            w.mg.vals_s[l] = bump.take<double>(zl * B);
-            w.mg.dinv[l] = bump.take<double>(nl * B);
-            w.mg.b[l] = bump.take<double>(nl * 3 * B);
-            w.mg.t[l] = bump.take<double>(nl * 3 * B);
-            w.mg.z[l] = bump.take<double>(nl * 3 * B);
+            w.mg.vals[l] = bump.take<mgf>(zl * B);
+            w.mg.vals_s[l] = bump.take<mgf>(zl * B);
+            w.mg.dinv[l] = bump.take<mgf>(nl * B);
+            w.mg.b[l] = bump.take<mgf>(nl * 3 * B);
+            w.mg.t[l] = bump.take<mgf>(nl * 3 * B);
+            w.mg.z[l] = bump.take<mgf>(nl * 3 * B);
         }
         int64_t nc = mg_n[mg_levels - 1];
         if (nc <= kCoarsestDense) {
             w.mg.Lf = bump.take<double>(nc * (nc + 1) / 2 * B);
-            w.mg.inv = bump.take<double>(nc * nc * B);
+            w.mg.inv_work = bump.take<double>(nc * nc * B);
+            w.mg.inv = bump.take<mgf>(nc * nc * B);
+        } else {
+            w.mg.tmp = bump.take<mgf>(nc * 3 * B);
         }
-        else w.mg.tmp = bump.take<double>(nc * 3 * B);
     }
     w.qT = bump.take<double>(E * B);
     w.vals = bump.take<double>(nnz * B);
@@ -1121,38 +1153,45 @@ static MgMat mg_mat(const PlanDev& P, const MgDev& M, const PcgBuffers& w, int l
     MgMat A{};
     if (level == 0) {
         A.n = P.nf; A.ell_w = P.ell_w; A.rowptr = P.rowptr; A.ell_col = P.ell_col;
-        A.vals = w.vals; A.dinv = w.dinv;
     } else {
         const MgLevelDev& L = M.lv[level - 1];
         A.n = L.n; A.ell_w = L.ell_w; A.rowptr = L.rowptr; A.ell_col = L.ell_col;
-        A.vals = w.mg.vals[level]; A.dinv = w.mg.dinv[level];
     }
+    A.vals = w.mg.vals[level];
     A.vals_s = w.mg.vals_s[level];
+    A.dinv = w.mg.dinv[level];
     return A;
 }
 
 // numerical set-up of the hierarchy for the assembled K of this evaluation (once per evaluation)
 static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, cudaStream_t st) {
     const int nl = M.n_levels;
+    {
+        LaneCfg c0 = rows_cfg(k_mg_prepare0, base, P.nf);
+        k_mg_prepare0<<<c0.nchunks * c0.nslabs, kThreads, 0, st>>>(P.nf, P.rowptr, P.ell_col, P.ell_w, c0, B, w.vals, w.dinv,
+                                                                    w.mg.vals[0], w.mg.vals_s[0], w.mg.dinv[0]);
+        DFDM_LAUNCH_OK("k_mg_prepare0");
+    }
     for (int l = 0; l < nl; ++l) {
         const MgLevelDev& L = M.lv[l];
-        MgMat Af = mg_mat(P, M, w, l);
-        LaneCfg c1 = rows_cfg(k_mg_scale, base, Af.n);
-        k_mg_scale<<<c1.nchunks * c1.nslabs, kThreads, 0, st>>>(Af.n, Af.rowptr, Af.ell_col, Af.ell_w, c1, B, Af.vals, Af.dinv,
-                                                                 w.mg.vals_s[l]);
-        DFDM_LAUNCH_OK("k_mg_scale");
         LaneCfg c2 = rows_cfg(k_mg_galerkin, base, L.nnz);
-        k_mg_galerkin<<<c2.nchunks * c2.nslabs, kThreads, 0, st>>>(L, c2, B, Af.vals, w.mg.vals[l + 1]);
+        k_mg_galerkin<<<c2.nchunks * c2.nslabs, kThreads, 0, st>>>(L, c2, B, w.mg.vals[l], w.mg.vals[l + 1]);
         DFDM_LAUNCH_OK("k_mg_galerkin");
         LaneCfg c3 = rows_cfg(k_mg_dinv, base, L.n);
         k_mg_dinv<<<c3.nchunks * c3.nslabs, kThreads, 0, st>>>(L.n, L.diagslot, c3, B, w.mg.vals[l + 1], w.mg.dinv[l + 1]);
         DFDM_LAUNCH_OK("k_mg_dinv");
+        if (l + 1 < nl) {
+            LaneCfg c1 = rows_cfg(k_mg_scale, base, L.n);
+            k_mg_scale<<<c1.nchunks * c1.nslabs, kThreads, 0, st>>>(L.n, L.rowptr, L.ell_col, L.ell_w, c1, B, w.mg.vals[l + 1],
+                                                                     w.mg.dinv[l + 1], w.mg.vals_s[l + 1]);
+            DFDM_LAUNCH_OK("k_mg_scale");
+        }
     }
     const MgLevelDev& C = M.lv[nl - 1];
     if (w.mg.Lf) {
         k_mg_coarsest_factor<<<(B + 63) / 64, 64, 0, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.Lf);
         DFDM_LAUNCH_OK("k_mg_coarsest_factor");
-        k_mg_coarsest_inverse<<<(C.n * B + 127) / 128, 128, 0, st>>>(C.n, B, w.mg.Lf, w.mg.inv);
+        k_mg_coarsest_inverse<<<(C.n * B + 127) / 128, 128, 0, st>>>(C.n, B, w.mg.Lf, w.mg.inv_work, w.mg.inv);
         DFDM_LAUNCH_OK("k_mg_coarsest_inverse");
     }
     return DFDM_OK;
@@ -1162,14 +1201,19 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
 static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
                      size_t& used, MgParams mp) {
     const int nl = M.n_levels;
-    w.mg.b[0] = w.r;
-    w.mg.t[0] = w.Ap;           // Ap is dead between the update and the next SpMV
+    w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     for (int l = 0; l < nl; ++l) {
         MgMat A = mg_mat(P, M, w, l);
-        LaneCfg c = rows_cfg(k_mg_down, base, M.lv[l].n);
-        k_mg_down<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
-        DFDM_LAUNCH_OK("k_mg_down");
-        if (l == 0) prof_mark(st, 3, used);
+        if (l == 0) {
+            LaneCfg c = rows_cfg(k_mg_down<double>, base, M.lv[l].n);
+            k_mg_down<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
+            DFDM_LAUNCH_OK("k_mg_down");
+            prof_mark(st, 3, used);
+        } else {
+            LaneCfg c = rows_cfg(k_mg_down<mgf>, base, M.lv[l].n);
+            k_mg_down<mgf><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
+            DFDM_LAUNCH_OK("k_mg_down");
+        }
     }
     const MgLevelDev& C = M.lv[nl - 1];
     if (w.mg.Lf) {
@@ -1182,12 +1226,19 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
     }
     for (int l = nl - 1; l >= 0; --l) {
         MgMat A = mg_mat(P, M, w, l);
-        LaneCfg c = rows_cfg(k_mg_up, base, A.n);
-        if (l == 0) prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
-        k_mg_up<<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
-                                                          l == 0 ? 1 : 0, first, mp);
-        DFDM_LAUNCH_OK("k_mg_up");
-        if (l == 0) prof_mark(st, 4, used);
+        if (l == 0) {
+            prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
+            LaneCfg c = rows_cfg(k_mg_up<double>, base, A.n);
+            k_mg_up<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
+                                                                      1, first, mp);
+            DFDM_LAUNCH_OK("k_mg_up");
+            prof_mark(st, 4, used);
+        } else {
+            LaneCfg c = rows_cfg(k_mg_up<mgf>, base, A.n);
+            k_mg_up<mgf><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
+                                                                   0, first, mp);
+            DFDM_LAUNCH_OK("k_mg_up");
+        }
     }
     return DFDM_OK;
 }
@@ -1195,7 +1246,7 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
 static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
                      cudaStream_t st, int32_t* host_flag, int* iters_out) {
     const bool mg = M != nullptr && M->n_levels > 0;
-    MgParams mp{opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault, opt.mg_over > 0 ? opt.mg_over : kMgOverDefault};
+    MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault), (float)(opt.mg_over > 0 ? opt.mg_over : kMgOverDefault)};
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
     const LaneCfg cfg_spmv = one_wave(k_pcg_spmv, base, P.nf, kThreads);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
