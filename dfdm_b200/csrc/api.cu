@@ -13,16 +13,19 @@ void profile_read(double* ms, long long* count);
 
 // ---- device mirrors ------------------------------------------------------------------------------
 
-static int upload_plan(const Plan& P, int device, PlanDev& out) {
+static int upload_plan(const Plan& P, int device, PlanDev& out, PlanDev& out_pcg) {
     std::lock_guard<std::mutex> lock(P.mu);
     auto it = P.dev.find(device);
     if (it != P.dev.end()) {
         out = it->second;
+        out_pcg = P.dev_pcg[device];
         return DFDM_OK;
     }
     const std::vector<int32_t>* arrays[] = {&P.edges, &P.node_src, &P.free_nodes, &P.rowptr, &P.colidx, &P.diagslot,
                                             &P.finc_ptr, &P.finc_edge, &P.finc_code, &P.ninc_ptr, &P.ninc_edge, &P.ninc_sign,
-                                            &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code, &P.ell_col, &P.ell_slot};
+                                            &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code, &P.ell_col,
+                                            &P.pg.free_nodes, &P.pg.node_src, &P.pg.rowptr, &P.pg.colidx, &P.pg.diagslot, &P.pg.ell_col,
+                                            &P.pg.finc_ptr, &P.pg.finc_edge, &P.pg.finc_code};
     constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
     int64_t offs[NA], total = 0;
     for (int k = 0; k < NA; ++k) {
@@ -40,10 +43,16 @@ static int upload_plan(const Plan& P, int device, PlanDev& out) {
     d.edges = at(0); d.node_src = at(1); d.free_nodes = at(2); d.rowptr = at(3); d.colidx = at(4); d.diagslot = at(5);
     d.finc_ptr = at(6); d.finc_edge = at(7); d.finc_code = at(8); d.ninc_ptr = at(9); d.ninc_edge = at(10); d.ninc_sign = at(11);
     d.perm = at(12); d.pos = at(13); d.sinc_ptr = at(14); d.sinc_edge = at(15); d.sinc_code = at(16);
-    d.ell_w = P.ell_w; d.ell_col = at(17); d.ell_slot = at(18);
+    d.ell_w = P.ell_w; d.ell_col = at(17);
     P.dev[device] = d;
+    PlanDev g = d;                                    // the PCG path's view: same network, rows in its own order
+    g.free_nodes = at(18); g.node_src = at(19); g.rowptr = at(20); g.colidx = at(21); g.diagslot = at(22);
+    g.ell_w = P.pg.ell_w; g.ell_col = at(23); g.finc_ptr = at(24); g.finc_edge = at(25); g.finc_code = at(26);
+    g.perm = nullptr; g.pos = nullptr; g.sinc_ptr = nullptr; g.sinc_edge = nullptr; g.sinc_code = nullptr;
+    P.dev_pcg[device] = g;
     P.dev_block[device] = block;
     out = d;
+    out_pcg = g;
     return DFDM_OK;
 }
 
@@ -142,7 +151,7 @@ static int dispatch(const dfdm_plan* plan, const dfdm_goalprog* prog, Eval& ev, 
     }
     int device = 0;
     DFDM_CUDA_OK(cudaGetDevice(&device));
-    int rc = upload_plan(*plan, device, ev.P);
+    int rc = upload_plan(*plan, device, ev.P, ev.Pg);
     if (rc) return rc;
     rc = upload_mg(*plan, device, ev.M);
     if (rc) return rc;

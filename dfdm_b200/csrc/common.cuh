@@ -35,7 +35,8 @@ extern std::atomic<long long> g_launches;
 
 // One evaluation request, resolved to device pointers.  All batch arrays are design-major.
 struct Eval {
-    PlanDev P;
+    PlanDev P;                     // rows in ascending free order (direct path, ABI)
+    PlanDev Pg;                    // rows in the PCG path's hierarchical order
     MgDev M;
     GoalProgDev G;
     bool has_prog = false;

@@ -14,6 +14,7 @@
 // Reference being replaced: np.linalg.solve in src/dfdm/equilibrium/model.py:55 (for networks whose
 // banded factor does not fit shared memory) plus the assembly of model.py:50-54 and the
 // post-processing of model.py:21-34, batched.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -25,7 +26,14 @@ struct LaneCfg {
     int nchunks;   // ceil(B / lanes)
     int nslabs;    // CTAs per chunk
     int rstep;     // rows handled per CTA iteration = blockDim / lanes
+    int tile;      // consecutive rows a CTA works through before it jumps (multiple of rstep): with the hierarchical
+                   // row order a tile is a compact patch, so its neighbour gathers are served by L1
 };
+
+// rows of this thread: tiles slab, slab + nslabs, ...; inside a tile rows rl, rl + rstep, ...
+#define TILE_ROWS(f, n)                                                                              \
+    for (int _t0 = slab * cfg.tile; _t0 < (n); _t0 += cfg.nslabs * cfg.tile)                          \
+        for (int f = _t0 + rl, _te = min((n), _t0 + cfg.tile); f < _te; f += cfg.rstep)
 
 constexpr int kThreads = 256;
 
@@ -286,15 +294,11 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
         const size_t sB = (size_t)B;
         const double* pb = p + b;
         const double* vb = vals + b;
-        int col[kSpmvBatch];
-        int f = row0, k0 = 0, k1 = 0;
-        if (f < P.nf) {
-            k0 = P.rowptr[f];
-            k1 = P.rowptr[f + 1];
+        TILE_ROWS(f, P.nf) {
+            const int k0 = P.rowptr[f], k1 = P.rowptr[f + 1];
+            int col[kSpmvBatch];
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
-        }
-        while (f < P.nf) {
             double a[kSpmvBatch], x0[kSpmvBatch], x1[kSpmvBatch], x2[kSpmvBatch];
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) {
@@ -306,16 +310,6 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
             }
             const size_t od = (size_t)f * 3 * sB + b;
             const double d0 = p[od], d1 = p[od + sB], d2 = p[od + 2 * sB];
-            const int fn = f + rstride;
-#if DFDM_SPMV_PREFETCH
-            int ncol[kSpmvBatch], nk0 = 0, nk1 = 0;
-            if (fn < P.nf) {
-                nk0 = P.rowptr[fn];
-                nk1 = P.rowptr[fn + 1];
-#pragma unroll
-                for (int u = 0; u < kSpmvBatch; ++u) ncol[u] = u < W ? P.ell_col[(size_t)fn * W + u] : fn;
-            }
-#endif
             double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) {
@@ -336,20 +330,6 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
             v[0] += d0 * a0;
             v[1] += d1 * a1;
             v[2] += d2 * a2;
-            f = fn;
-#if DFDM_SPMV_PREFETCH
-            k0 = nk0;
-            k1 = nk1;
-#pragma unroll
-            for (int u = 0; u < kSpmvBatch; ++u) col[u] = ncol[u];
-#else
-            if (f < P.nf) {
-                k0 = P.rowptr[f];
-                k1 = P.rowptr[f + 1];
-#pragma unroll
-                for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
-            }
-#endif
         }
     }
     if (publish_partials<3>(v, cfg, B, S.partial, S.tickets)) {
@@ -555,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, 
     LANE_SETUP();
     if (!live) return;
     const size_t sB = (size_t)B;
-    for (int I = row0; I < L.n; I += rstride) {
+    TILE_ROWS(I, L.n) {
         float rc[3] = {0.0f, 0.0f, 0.0f};
         for (int m = L.mem_ptr[I]; m < L.mem_ptr[I + 1]; ++m) {
             int f = L.mem_idx[m];
@@ -585,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
     double v[3] = {0, 0, 0};
     if (live) {
         const size_t sB = (size_t)B;
-        for (int f = row0; f < A.n; f += rstride) {
+        TILE_ROWS(f, A.n) {
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
             // s = (K P e)_f: gather the coarse solution through the aggregate map
             float sacc[3] = {0.0f, 0.0f, 0.0f};
@@ -983,6 +963,7 @@ static LaneCfg one_wave(Kernel kernel, const LaneCfg& base, int rows, int thread
     LaneCfg cfg = base;
     int want = std::max(1, (sms * std::max(per_sm, 1)) / base.nchunks);
     int rows_cta = threads == kVecThreads ? (kVecThreads >> base.shift) / 3 : (kThreads >> base.shift);
+    cfg.tile = rows_cta;
     int most = (rows + rows_cta - 1) / rows_cta;
     cfg.nslabs = std::max(1, std::min(std::min(want, most), 2048));
     return cfg;
@@ -1145,9 +1126,20 @@ static void prof_resolve(size_t used) {
     }
 }
 
-// grid for a 256-thread row kernel over `rows` rows: one wave of that kernel
+static int tile_factor(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    int f = v ? std::atoi(v) : fallback;
+    return f >= 1 && f <= 64 ? f : fallback;
+}
+
+// grid for a 256-thread row kernel over `rows` rows: one wave of that kernel; `tiles` > 1 makes a CTA work through
+// that many consecutive row groups (a compact patch in the hierarchical order) before it jumps
 template <typename Kernel>
-static LaneCfg rows_cfg(Kernel kernel, const LaneCfg& base, int rows) { return one_wave(kernel, base, rows, kThreads); }
+static LaneCfg rows_cfg(Kernel kernel, const LaneCfg& base, int rows, int tiles = 1) {
+    LaneCfg cfg = one_wave(kernel, base, rows, kThreads);
+    cfg.tile = cfg.rstep * tiles;
+    return cfg;
+}
 
 static MgMat mg_mat(const PlanDev& P, const MgDev& M, const PcgBuffers& w, int level) {
     MgMat A{};
@@ -1205,7 +1197,8 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
     for (int l = 0; l < nl; ++l) {
         MgMat A = mg_mat(P, M, w, l);
         if (l == 0) {
-            LaneCfg c = rows_cfg(k_mg_down<double>, base, M.lv[l].n);
+            static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1);
+            LaneCfg c = rows_cfg(k_mg_down<double>, base, M.lv[l].n, down_tiles);
             k_mg_down<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
             DFDM_LAUNCH_OK("k_mg_down");
             prof_mark(st, 3, used);
@@ -1228,7 +1221,8 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
         MgMat A = mg_mat(P, M, w, l);
         if (l == 0) {
             prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
-            LaneCfg c = rows_cfg(k_mg_up<double>, base, A.n);
+            static const int up_tiles = tile_factor("DFDM_TILE_UP", 4);
+            LaneCfg c = rows_cfg(k_mg_up<double>, base, A.n, up_tiles);
             k_mg_up<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
                                                                       1, first, mp);
             DFDM_LAUNCH_OK("k_mg_up");
@@ -1248,7 +1242,8 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
     const bool mg = M != nullptr && M->n_levels > 0;
     MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault), (float)(opt.mg_over > 0 ? opt.mg_over : kMgOverDefault)};
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
-    const LaneCfg cfg_spmv = one_wave(k_pcg_spmv, base, P.nf, kThreads);
+    static const int spmv_tiles = tile_factor("DFDM_TILE_SPMV", 4);
+    const LaneCfg cfg_spmv = rows_cfg(k_pcg_spmv, base, P.nf, spmv_tiles);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
     const LaneCfg cfg_dir = one_wave(k_pcg_direction, base, P.nf, kVecThreads);
     int grid = cfg.nchunks * cfg.nslabs;
@@ -1313,7 +1308,7 @@ static int to_design_major(const double* src, double* dst, int B, int64_t rows, 
 }
 
 int run_pcg(Eval& ev) {
-    const PlanDev& P = ev.P;
+    const PlanDev& P = ev.Pg;
     const int B = ev.B;
     cudaStream_t st = ev.stream;
     LaneCfg cfg{};

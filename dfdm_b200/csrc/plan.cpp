@@ -175,66 +175,183 @@ Graph match_pass(const Graph& g, std::vector<int32_t>& match) {
 
 }  // namespace
 
-static void build_multigrid(Plan& P) {
+// aggregation decisions only: agg[l] maps the rows of level l to the rows of level l+1
+static std::vector<std::vector<int32_t>> aggregate_levels(int n, const std::vector<int32_t>& rowptr,
+                                                          const std::vector<int32_t>& colidx, std::vector<int>& sizes) {
     constexpr int kCoarsest = 24;
-    int n = P.nf;
-    std::vector<int32_t> rowptr = P.rowptr, colidx = P.colidx;
+    std::vector<std::vector<int32_t>> aggs;
     Graph g = graph_from_csr(n, rowptr, colidx);
-    while (n > kCoarsest && (int)P.mg.size() < kMaxMgLevels) {
+    sizes.assign(1, n);
+    while (n > kCoarsest && (int)aggs.size() < kMaxMgLevels) {
         std::vector<int32_t> m1, m2;
         Graph g1 = match_pass(g, m1);
         Graph g2 = match_pass(g1, m2);
         if (g2.n >= n) break;                                  // no edges left to coarsen along
-        MgLevel L;
-        L.n_fine = n;
-        L.n = g2.n;
-        L.agg.resize(n);
-        for (int i = 0; i < n; ++i) L.agg[i] = m2[m1[i]];
-        L.mem_ptr.assign(L.n + 1, 0);
-        for (int i = 0; i < n; ++i) L.mem_ptr[L.agg[i] + 1]++;
-        for (int a = 0; a < L.n; ++a) L.mem_ptr[a + 1] += L.mem_ptr[a];
-        L.mem_idx.resize(n);
-        {
-            std::vector<int32_t> cur(L.mem_ptr.begin(), L.mem_ptr.end() - 1);
-            for (int i = 0; i < n; ++i) L.mem_idx[cur[L.agg[i]]++] = i;
+        std::vector<int32_t> agg(n);
+        for (int i = 0; i < n; ++i) agg[i] = m2[m1[i]];
+        aggs.push_back(std::move(agg));
+        n = g2.n;
+        sizes.push_back(n);
+        g = std::move(g2);
+    }
+    return aggs;
+}
+
+// structures of one coarse level from the fine pattern and a prescribed aggregate map
+static MgLevel build_level(int n, const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx,
+                           const std::vector<int32_t>& agg, int nc) {
+    MgLevel L;
+    L.n_fine = n;
+    L.n = nc;
+    L.agg = agg;
+    L.mem_ptr.assign(L.n + 1, 0);
+    for (int i = 0; i < n; ++i) L.mem_ptr[L.agg[i] + 1]++;
+    for (int a = 0; a < L.n; ++a) L.mem_ptr[a + 1] += L.mem_ptr[a];
+    L.mem_idx.resize(n);
+    {
+        std::vector<int32_t> cur(L.mem_ptr.begin(), L.mem_ptr.end() - 1);
+        for (int i = 0; i < n; ++i) L.mem_idx[cur[L.agg[i]]++] = i;
+    }
+    // coarse pattern and the Galerkin gather lists from the fine pattern
+    const int nnz_f = rowptr[n];
+    std::vector<std::pair<int64_t, int32_t>> keyed(nnz_f);   // (coarse row * nc + coarse col, fine slot)
+    for (int i = 0; i < n; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) keyed[k] = {(int64_t)L.agg[i] * L.n + L.agg[colidx[k]], k};
+    std::sort(keyed.begin(), keyed.end());
+    L.rowptr.assign(L.n + 1, 0);
+    L.gal_ptr.push_back(0);
+    L.gal_src.resize(nnz_f);
+    L.diagslot.assign(L.n, -1);
+    for (int k = 0; k < nnz_f;) {
+        int e = k;
+        while (e < nnz_f && keyed[e].first == keyed[k].first) {
+            L.gal_src[e] = keyed[e].second;
+            ++e;
         }
-        // coarse pattern and the Galerkin gather lists from the fine pattern
-        const int nnz_f = rowptr[n];
-        std::vector<std::pair<int64_t, int32_t>> keyed(nnz_f);   // (coarse row * nc + coarse col, fine slot)
-        for (int i = 0; i < n; ++i)
-            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
-                keyed[k] = {(int64_t)L.agg[i] * L.n + L.agg[colidx[k]], k};
-        std::sort(keyed.begin(), keyed.end());
-        L.rowptr.assign(L.n + 1, 0);
-        L.gal_ptr.push_back(0);
-        L.gal_src.resize(nnz_f);
-        L.diagslot.assign(L.n, -1);
-        for (int k = 0; k < nnz_f;) {
-            int e = k;
-            while (e < nnz_f && keyed[e].first == keyed[k].first) {
-                L.gal_src[e] = keyed[e].second;
-                ++e;
-            }
-            int row = (int)(keyed[k].first / L.n), col = (int)(keyed[k].first % L.n);
-            if (row == col) L.diagslot[row] = (int)L.colidx.size();
-            L.colidx.push_back(col);
-            L.rowptr[row + 1]++;
-            L.gal_ptr.push_back(e);
-            k = e;
+        int row = (int)(keyed[k].first / L.n), col = (int)(keyed[k].first % L.n);
+        if (row == col) L.diagslot[row] = (int)L.colidx.size();
+        L.colidx.push_back(col);
+        L.rowptr[row + 1]++;
+        L.gal_ptr.push_back(e);
+        k = e;
+    }
+    for (int a = 0; a < L.n; ++a) L.rowptr[a + 1] += L.rowptr[a];
+    L.nnz = (int)L.colidx.size();
+    for (int a = 0; a < L.n; ++a) L.ell_w = std::max(L.ell_w, L.rowptr[a + 1] - L.rowptr[a]);
+    L.ell_col.assign((size_t)L.n * L.ell_w, 0);
+    for (int a = 0; a < L.n; ++a)
+        for (int u = 0; u < L.ell_w; ++u) {
+            int k = L.rowptr[a] + u;
+            L.ell_col[(size_t)a * L.ell_w + u] = k < L.rowptr[a + 1] ? L.colidx[k] : a;
         }
-        for (int a = 0; a < L.n; ++a) L.rowptr[a + 1] += L.rowptr[a];
-        L.nnz = (int)L.colidx.size();
-        for (int a = 0; a < L.n; ++a) L.ell_w = std::max(L.ell_w, L.rowptr[a + 1] - L.rowptr[a]);
-        L.ell_col.assign((size_t)L.n * L.ell_w, 0);
-        for (int a = 0; a < L.n; ++a)
-            for (int u = 0; u < L.ell_w; ++u) {
-                int k = L.rowptr[a] + u;
-                L.ell_col[(size_t)a * L.ell_w + u] = k < L.rowptr[a + 1] ? L.colidx[k] : a;
-            }
+    return L;
+}
+
+// Pattern of K, its padded copy and the gather form of the scatter-add for a given order of the free nodes.
+static void build_rowset(const Plan& P, const std::vector<int32_t>& free_nodes, RowSet& R) {
+    const int n = P.n, nf = (int)free_nodes.size();
+    const int32_t* edges = P.edges.data();
+    R.nf = nf;
+    R.free_nodes = free_nodes;
+    R.node_src = P.node_src;                                   // fixed nodes keep -1 - k
+    for (int r = 0; r < nf; ++r) R.node_src[free_nodes[r]] = r;
+    (void)n;
+    R.rowptr.assign(nf + 1, 0);
+    std::vector<std::vector<int32_t>> cols(nf);
+    for (int f = 0; f < nf; ++f) {
+        int i = free_nodes[f];
+        auto& c = cols[f];
+        c.push_back(f);
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
+            int e = P.ninc_edge[k];
+            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
+            if (R.node_src[other] >= 0) c.push_back(R.node_src[other]);
+        }
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        R.rowptr[f + 1] = R.rowptr[f] + (int)c.size();
+    }
+    R.nnz = R.rowptr[nf];
+    R.colidx.resize(R.nnz);
+    R.diagslot.resize(nf);
+    for (int f = 0; f < nf; ++f) {
+        std::copy(cols[f].begin(), cols[f].end(), R.colidx.begin() + R.rowptr[f]);
+        R.diagslot[f] = R.rowptr[f] + (int)(std::lower_bound(cols[f].begin(), cols[f].end(), f) - cols[f].begin());
+    }
+    auto slot_of = [&](int row, int col) {
+        auto b = R.colidx.begin() + R.rowptr[row], e = R.colidx.begin() + R.rowptr[row + 1];
+        return (int)(std::lower_bound(b, e, col) - R.colidx.begin());
+    };
+    // padded copy of the pattern for the SpMV kernels (indices depend on the row number only)
+    R.ell_w = 0;
+    for (int f = 0; f < nf; ++f) R.ell_w = std::max(R.ell_w, R.rowptr[f + 1] - R.rowptr[f]);
+    R.ell_col.assign((size_t)nf * R.ell_w, 0);
+    for (int f = 0; f < nf; ++f)
+        for (int u = 0; u < R.ell_w; ++u) {
+            int k = R.rowptr[f] + u;
+            R.ell_col[(size_t)f * R.ell_w + u] = k < R.rowptr[f + 1] ? R.colidx[k] : f;
+        }
+    // free-row incidence (gather form of the scatter-add: one segment per row, fixed order)
+    R.finc_ptr.assign(nf + 1, 0);
+    for (int f = 0; f < nf; ++f) {
+        int i = free_nodes[f];
+        R.finc_ptr[f + 1] = R.finc_ptr[f] + (P.ninc_ptr[i + 1] - P.ninc_ptr[i]);
+    }
+    R.finc_edge.resize(R.finc_ptr[nf]);
+    R.finc_code.resize(R.finc_ptr[nf]);
+    for (int f = 0; f < nf; ++f) {
+        int i = free_nodes[f];
+        int o = R.finc_ptr[f];
+        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k, ++o) {
+            int e = P.ninc_edge[k];
+            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
+            R.finc_edge[o] = e;
+            R.finc_code[o] = R.node_src[other] >= 0 ? slot_of(f, R.node_src[other]) : R.node_src[other];
+        }
+        // parallel edges share a slot: keep them adjacent (code, then edge index) so the row sums them in a fixed order
+        std::vector<std::pair<int32_t, int32_t>> seg;
+        for (int k = R.finc_ptr[f]; k < R.finc_ptr[f + 1]; ++k) seg.emplace_back(R.finc_code[k], R.finc_edge[k]);
+        std::sort(seg.begin(), seg.end());
+        for (int k = R.finc_ptr[f], t = 0; k < R.finc_ptr[f + 1]; ++k, ++t) {
+            R.finc_code[k] = seg[t].first;
+            R.finc_edge[k] = seg[t].second;
+        }
+    }
+}
+
+// The PCG path numbers its rows hierarchically: rows of one aggregate are contiguous, aggregates of one
+// parent aggregate are contiguous, and so on up the hierarchy, so that a run of consecutive rows is a
+// compact patch of the network at every level and neighbour gathers hit L1 instead of L2.
+static void build_pcg_order(Plan& P) {
+    std::vector<int> sizes;
+    std::vector<std::vector<int32_t>> aggs = aggregate_levels(P.nf, P.rowptr, P.colidx, sizes);
+    const int nl = (int)aggs.size();
+    // newid[l][old row of level l] = position in the hierarchical order of level l (top-down)
+    std::vector<std::vector<int32_t>> newid(nl + 1);
+    newid[nl].resize(sizes[nl]);
+    std::iota(newid[nl].begin(), newid[nl].end(), 0);
+    for (int l = nl - 1; l >= 0; --l) {
+        std::vector<int32_t> order(sizes[l]);
+        std::iota(order.begin(), order.end(), 0);
+        const auto& parent = aggs[l];
+        const auto& ppos = newid[l + 1];
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ppos[parent[a]] < ppos[parent[b]]; });
+        newid[l].resize(sizes[l]);
+        for (int k = 0; k < sizes[l]; ++k) newid[l][order[k]] = k;
+    }
+    P.pg_perm.resize(P.nf);
+    for (int f = 0; f < P.nf; ++f) P.pg_perm[newid[0][f]] = f;
+    std::vector<int32_t> free_nodes(P.nf);
+    for (int r = 0; r < P.nf; ++r) free_nodes[r] = P.free_nodes[P.pg_perm[r]];
+    build_rowset(P, free_nodes, P.pg);
+    // coarse levels on the relabelled rows with the relabelled aggregate maps
+    std::vector<int32_t> rowptr = P.pg.rowptr, colidx = P.pg.colidx;
+    for (int l = 0; l < nl; ++l) {
+        std::vector<int32_t> agg(sizes[l]);
+        for (int i = 0; i < sizes[l]; ++i) agg[newid[l][i]] = newid[l + 1][aggs[l][i]];
+        MgLevel L = build_level(sizes[l], rowptr, colidx, agg, sizes[l + 1]);
         rowptr = L.rowptr;
         colidx = L.colidx;
-        n = L.n;
-        g = std::move(g2);
         P.mg.push_back(std::move(L));
     }
 }
@@ -298,48 +415,25 @@ int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fix
         }
     }
 
-    // CSR pattern of K = C_f^T Q C_f in free order
+    // pattern of K = C_f^T Q C_f in ascending free order (the order of the reference; exposed through the ABI)
     const int nf = P.nf;
-    P.rowptr.assign(nf + 1, 0);
-    std::vector<std::vector<int32_t>> cols(nf);
-    for (int f = 0; f < nf; ++f) {
-        int i = P.free_nodes[f];
-        auto& c = cols[f];
-        c.push_back(f);
-        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
-            int e = P.ninc_edge[k];
-            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
-            if (P.node_src[other] >= 0) c.push_back(P.node_src[other]);
-        }
-        std::sort(c.begin(), c.end());
-        c.erase(std::unique(c.begin(), c.end()), c.end());
-        P.rowptr[f + 1] = P.rowptr[f] + (int)c.size();
-    }
-    P.nnz = P.rowptr[nf];
-    P.colidx.resize(P.nnz);
-    P.diagslot.resize(nf);
-    for (int f = 0; f < nf; ++f) {
-        std::copy(cols[f].begin(), cols[f].end(), P.colidx.begin() + P.rowptr[f]);
-        P.diagslot[f] = P.rowptr[f] + (int)(std::lower_bound(cols[f].begin(), cols[f].end(), f) - cols[f].begin());
-    }
+    RowSet nat;
+    build_rowset(P, P.free_nodes, nat);
+    P.nnz = nat.nnz;
+    P.rowptr = nat.rowptr;
+    P.colidx = nat.colidx;
+    P.diagslot = nat.diagslot;
+    P.ell_w = nat.ell_w;
+    P.ell_col = nat.ell_col;
+    P.finc_ptr = nat.finc_ptr;
+    P.finc_edge = nat.finc_edge;
+    P.finc_code = nat.finc_code;
     auto slot_of = [&](int row, int col) {
         auto b = P.colidx.begin() + P.rowptr[row], e = P.colidx.begin() + P.rowptr[row + 1];
         return (int)(std::lower_bound(b, e, col) - P.colidx.begin());
     };
 
-    // padded copy of the pattern for the SpMV kernels (indices depend on the row number only)
-    for (int f = 0; f < nf; ++f) P.ell_w = std::max(P.ell_w, P.rowptr[f + 1] - P.rowptr[f]);
-    P.ell_col.assign((size_t)nf * P.ell_w, 0);
-    P.ell_slot.assign((size_t)nf * P.ell_w, -1);
-    for (int f = 0; f < nf; ++f)
-        for (int u = 0; u < P.ell_w; ++u) {
-            int k = P.rowptr[f] + u;
-            bool real = k < P.rowptr[f + 1];
-            P.ell_col[(size_t)f * P.ell_w + u] = real ? P.colidx[k] : f;
-            P.ell_slot[(size_t)f * P.ell_w + u] = real ? k : -1;
-        }
-
-    build_multigrid(P);
+    build_pcg_order(P);
 
     // per-edge scatter slots (uu, vv, uv, vu)
     P.edge_slots.assign(4 * (size_t)E, -1);
@@ -352,33 +446,6 @@ int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fix
         if (fu >= 0 && fv >= 0) {
             P.edge_slots[4 * e + 2] = slot_of(fu, fv);
             P.edge_slots[4 * e + 3] = slot_of(fv, fu);
-        }
-    }
-
-    // free-row incidence (gather form of the scatter-add: one segment per row, fixed order)
-    P.finc_ptr.assign(nf + 1, 0);
-    for (int f = 0; f < nf; ++f) {
-        int i = P.free_nodes[f];
-        P.finc_ptr[f + 1] = P.finc_ptr[f] + (P.ninc_ptr[i + 1] - P.ninc_ptr[i]);
-    }
-    P.finc_edge.resize(P.finc_ptr[nf]);
-    P.finc_code.resize(P.finc_ptr[nf]);
-    for (int f = 0; f < nf; ++f) {
-        int i = P.free_nodes[f];
-        int o = P.finc_ptr[f];
-        for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k, ++o) {
-            int e = P.ninc_edge[k];
-            int other = edges[2 * e] == i ? edges[2 * e + 1] : edges[2 * e];
-            P.finc_edge[o] = e;
-            P.finc_code[o] = P.node_src[other] >= 0 ? slot_of(f, P.node_src[other]) : P.node_src[other];
-        }
-        // parallel edges share a slot: keep them adjacent (code, then edge index) so the row sums them in a fixed order
-        std::vector<std::pair<int32_t, int32_t>> seg;
-        for (int k = P.finc_ptr[f]; k < P.finc_ptr[f + 1]; ++k) seg.emplace_back(P.finc_code[k], P.finc_edge[k]);
-        std::sort(seg.begin(), seg.end());
-        for (int k = P.finc_ptr[f], t = 0; k < P.finc_ptr[f + 1]; ++k, ++t) {
-            P.finc_code[k] = seg[t].first;
-            P.finc_edge[k] = seg[t].second;
         }
     }
 

@@ -25,7 +25,6 @@ struct PlanDev {
     // the same pattern padded to ell_w entries per row: column (own row for padding); slots are rowptr[f] + u
     int ell_w = 0;
     const int32_t* ell_col = nullptr;     // [nf][ell_w]
-    const int32_t* ell_slot = nullptr;    // [nf][ell_w]
     // free-row incidence in free order: entry -> (edge, code) with code = CSR slot of the off-diagonal
     // (>= 0) or -1 - k when the neighbour is fixed node k (contributes to the right-hand side)
     const int32_t* finc_ptr = nullptr;    // [nf+1]
@@ -71,23 +70,35 @@ struct MgLevel {
     std::vector<int32_t> agg, mem_ptr, mem_idx, rowptr, colidx, ell_col, diagslot, gal_ptr, gal_src;
 };
 
+// The pattern of K and the assembly gather lists for one ordering of the free nodes.
+struct RowSet {
+    int nf = 0, nnz = 0, ell_w = 0;
+    std::vector<int32_t> free_nodes;     // [nf] node id of each row
+    std::vector<int32_t> node_src;       // [n]  row of a free node, or -1 - k for fixed node k
+    std::vector<int32_t> rowptr, colidx, diagslot, ell_col;
+    std::vector<int32_t> finc_ptr, finc_edge, finc_code;
+};
+
 struct Plan {
     int n = 0, E = 0, nf = 0, nx = 0, nnz = 0, w_nat = 0, w = 0;
     bool use_rcm = false;
     std::vector<int32_t> edges, free_nodes, fixed_nodes, freefixed, node_src;
     std::vector<int32_t> rowptr, colidx, diagslot, edge_slots;
     int ell_w = 0;
-    std::vector<int32_t> ell_col, ell_slot;
+    std::vector<int32_t> ell_col;
     std::vector<int32_t> finc_ptr, finc_edge, finc_code;
     std::vector<int32_t> ninc_ptr, ninc_edge, ninc_sign;
     std::vector<int32_t> perm, pos;
     std::vector<int32_t> sinc_ptr, sinc_edge, sinc_code;
-    std::vector<MgLevel> mg;              // coarse levels, finest first
+    RowSet pg;                            // rows in the PCG path's own (hierarchical, locality preserving) order
+    std::vector<int32_t> pg_perm;         // [nf] free index of each PCG row
+    std::vector<MgLevel> mg;              // coarse levels, finest first (built on the PCG row order)
     mutable std::map<int, MgDev> mg_dev;
 
     // lazily created device mirrors and cached arenas for the *_host entry points
     mutable std::mutex mu;
     mutable std::map<int, PlanDev> dev;
+    mutable std::map<int, PlanDev> dev_pcg;
     mutable std::map<int, void*> dev_block;
     struct Arena { void* ptr = nullptr; int64_t bytes = 0; };
     mutable std::map<int, Arena> arena;
