@@ -496,118 +496,198 @@ __global__ void __launch_bounds__(kThreads) k_mg_scale(int n, const int32_t* __r
     }
 }
 
+// V designs per thread (V = 2 when the batch is even): single-precision lanes then move 8 bytes per thread and
+// 256 bytes per warp request, the same as a double-precision lane - with V = 1 the V-cycle kernels keep the
+// request rate of the double-precision kernels but move half the bytes, and end up latency bound.
+template <int V> struct Vf { float v[V]; };
+__device__ __forceinline__ Vf<1> ldv1(const float* p) { Vf<1> r; r.v[0] = *p; return r; }
+__device__ __forceinline__ Vf<2> ldv2(const float* p) { float2 t = *reinterpret_cast<const float2*>(p); Vf<2> r; r.v[0] = t.x; r.v[1] = t.y; return r; }
+__device__ __forceinline__ Vf<1> ldv1(const double* p) { Vf<1> r; r.v[0] = (float)*p; return r; }
+__device__ __forceinline__ Vf<2> ldv2(const double* p) { double2 t = *reinterpret_cast<const double2*>(p); Vf<2> r; r.v[0] = (float)t.x; r.v[1] = (float)t.y; return r; }
+template <int V, typename T> __device__ __forceinline__ Vf<V> ldv(const T* p) { if constexpr (V == 1) return ldv1(p); else return ldv2(p); }
+template <int V> __device__ __forceinline__ void stv(float* p, const Vf<V>& x) {
+    if constexpr (V == 1) *p = x.v[0]; else *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]);
+}
+
+#define LANE_SETUP_V()                                                      \
+    const int cbl = 1 << cfg.shift;                                         \
+    const int chunk = blockIdx.x % cfg.nchunks;                             \
+    const int slab = blockIdx.x / cfg.nchunks;                              \
+    const int bl = threadIdx.x & (cbl - 1);                                 \
+    const int rl = threadIdx.x >> cfg.shift;                                \
+    const int b = (chunk * cbl + bl) * V;                                   \
+    const bool live = b < B;                                                \
+    (void)live; (void)chunk; (void)slab; (void)bl; (void)rl;
+
 // row product helper: acc[c] += sum_u val[k0+u] * vec[col(u)][c]; all loads of a batch issued before use
-template <typename TV>
+template <int V, typename TV>
 __device__ __forceinline__ void mg_row(const int32_t* __restrict__ ell_col, int W, int f, int k0, int len, const mgf* __restrict__ vb,
-                                       const TV* __restrict__ xb, size_t sB, float acc[3]) {
+                                       const TV* __restrict__ xb, size_t sB, Vf<V> acc[3]) {
     constexpr int U = 5;
     for (int u0 = 0; u0 < len; u0 += U) {
         int col[U];
-        float a[U];
-        TV x0[U], x1[U], x2[U];
+        Vf<V> a[U], x0[U], x1[U], x2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) col[u] = ell_col[(size_t)f * W + min(u0 + u, len - 1)];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            a[u] = u0 + u < len ? vb[(size_t)(k0 + u0 + u) * sB] : 0.0f;
+            if (u0 + u < len) a[u] = ldv<V>(vb + (size_t)(k0 + u0 + u) * sB);
+            else
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[u].v[v] = 0.0f;
             const TV* xj = xb + (size_t)col[u] * 3 * sB;
-            x0[u] = xj[0];
-            x1[u] = xj[sB];
-            x2[u] = xj[2 * sB];
+            x0[u] = ldv<V>(xj);
+            x1[u] = ldv<V>(xj + sB);
+            x2[u] = ldv<V>(xj + 2 * sB);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            acc[0] += a[u] * (float)x0[u];
-            acc[1] += a[u] * (float)x1[u];
-            acc[2] += a[u] * (float)x2[u];
-        }
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                acc[0].v[v] += a[u].v[v] * x0[u].v[v];
+                acc[1].v[v] += a[u].v[v] * x1[u].v[v];
+                acc[2].v[v] += a[u].v[v] * x2[u].v[v];
+            }
     }
 }
 
 // down pass of a level (operator A, right-hand side bvec of type TB: the double-precision CG residual on level 0,
 // single precision below): writes t = (K D^-1) b and the coarse right-hand side.  One thread per (coarse row,
-// design): it owns the aggregate, so the restriction needs no atomics.
-template <typename TB>
+// V designs): it owns the aggregate, so the restriction needs no atomics.
+template <typename TB, int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
                                                         mgf* __restrict__ t, mgf* __restrict__ b_coarse,
                                                         const int32_t* __restrict__ n_active, MgParams mp) {
     if (__ldcg(&n_active[1]) == 0) return;
-    LANE_SETUP();
+    LANE_SETUP_V();
     if (!live) return;
     const size_t sB = (size_t)B;
     TILE_ROWS(I, L.n) {
-        float rc[3] = {0.0f, 0.0f, 0.0f};
+        Vf<V> rc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < V; ++v) rc[c].v[v] = 0.0f;
         for (int m = L.mem_ptr[I]; m < L.mem_ptr[I + 1]; ++m) {
             int f = L.mem_idx[m];
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
-            float acc[3] = {0.0f, 0.0f, 0.0f};
-            mg_row<TB>(A.ell_col, A.ell_w, f, k0, len, A.vals_s + b, bvec + b, sB, acc);
+            Vf<V> acc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[c].v[v] = 0.0f;
+            mg_row<V, TB>(A.ell_col, A.ell_w, f, k0, len, A.vals_s + b, bvec + b, sB, acc);
             size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                t[o + c * sB] = acc[c];
-                rc[c] += (float)bvec[o + c * sB] - mp.omega * acc[c];
+                stv<V>(t + o + c * sB, acc[c]);
+                Vf<V> bc = ldv<V>(bvec + o + c * sB);
+#pragma unroll
+                for (int v = 0; v < V; ++v) rc[c].v[v] += bc.v[v] - mp.omega * acc[c].v[v];
             }
         }
         size_t oc = (size_t)I * 3 * sB + b;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) b_coarse[oc + c * sB] = rc[c];
+        for (int c = 0; c < 3; ++c) stv<V>(b_coarse + oc + c * sB, rc[c]);
     }
 }
 
 // up pass of a level: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
-template <typename TB>
+template <typename TB, int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
                                                       const mgf* __restrict__ t, const mgf* __restrict__ e_coarse,
                                                       mgf* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
     if (__ldcg(&S.n_active[1]) == 0) return;
-    LANE_SETUP();
-    double v[3] = {0, 0, 0};
+    LANE_SETUP_V();
+    double dsum[3][V];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) dsum[c][v] = 0.0;
     if (live) {
         const size_t sB = (size_t)B;
         TILE_ROWS(f, A.n) {
             int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
             // s = (K P e)_f: gather the coarse solution through the aggregate map
-            float sacc[3] = {0.0f, 0.0f, 0.0f};
+            Vf<V> sacc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int v = 0; v < V; ++v) sacc[c].v[v] = 0.0f;
             constexpr int U = 5;
             for (int u0 = 0; u0 < len; u0 += U) {
                 int cg[U];
-                float a[U], x0[U], x1[U], x2[U];
+                Vf<V> a[U], x0[U], x1[U], x2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) cg[u] = L.agg[A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)]];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    a[u] = u0 + u < len ? A.vals[(size_t)(k0 + u0 + u) * sB + b] : 0.0f;
+                    if (u0 + u < len) a[u] = ldv<V>(A.vals + (size_t)(k0 + u0 + u) * sB + b);
+                    else
+#pragma unroll
+                        for (int v = 0; v < V; ++v) a[u].v[v] = 0.0f;
                     const mgf* ej = e_coarse + (size_t)cg[u] * 3 * sB + b;
-                    x0[u] = ej[0];
-                    x1[u] = ej[sB];
-                    x2[u] = ej[2 * sB];
+                    x0[u] = ldv<V>(ej);
+                    x1[u] = ldv<V>(ej + sB);
+                    x2[u] = ldv<V>(ej + 2 * sB);
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    sacc[0] += a[u] * x0[u];
-                    sacc[1] += a[u] * x1[u];
-                    sacc[2] += a[u] * x2[u];
-                }
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        sacc[0].v[v] += a[u].v[v] * x0[u].v[v];
+                        sacc[1].v[v] += a[u].v[v] * x1[u].v[v];
+                        sacc[2].v[v] += a[u].v[v] * x2[u].v[v];
+                    }
             }
-            const float wd = mp.omega * A.dinv[(size_t)f * sB + b];
+            Vf<V> wd = ldv<V>(A.dinv + (size_t)f * sB + b);
             const mgf* ei = e_coarse + (size_t)L.agg[f] * 3 * sB + b;
             size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                TB bfull = bvec[o + c * sB];
-                float bc = (float)bfull;
-                float xn = wd * bc + mp.over * ei[c * sB];
-                float zc = xn + wd * (bc - mp.omega * t[o + c * sB] - mp.over * sacc[c]);
-                z[o + c * sB] = zc;
-                v[c] += (double)bfull * (double)zc;
+                Vf<V> bc = ldv<V>(bvec + o + c * sB), tc = ldv<V>(t + o + c * sB), ec = ldv<V>(ei + c * sB), zc;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    float w = mp.omega * wd.v[v];
+                    float xn = w * bc.v[v] + mp.over * ec.v[v];
+                    zc.v[v] = xn + w * (bc.v[v] - mp.omega * tc.v[v] - mp.over * sacc[c].v[v]);
+                    dsum[c][v] += (double)bc.v[v] * (double)zc.v[v];
+                }
+                stv<V>(z + o + c * sB, zc);
             }
         }
     }
     if (!dots) return;
-    if (publish_partials<3>(v, cfg, B, S.partial, S.tickets)) {
-        for (int idx = threadIdx.x; idx < 3 * cbl; idx += blockDim.x) {
-            int cc = idx >> cfg.shift, b2 = chunk * cbl + (idx & (cbl - 1));
+    // per-design partials: registers -> shared memory -> one partial per (slab, design); last CTA of the chunk finishes
+    __shared__ double red[3 * V][kThreads];
+    __shared__ int s_last;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) red[c * V + v][threadIdx.x] = dsum[c][v];
+    __syncthreads();
+    if (rl == 0 && live) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double s = 0.0;
+                for (int r = 0; r < cfg.rstep; ++r) s += red[c * V + v][(r << cfg.shift) + bl];
+                S.partial[((size_t)slab * 3 + c) * B + b + v] = s;
+            }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tk = atomicAdd(&S.tickets[chunk], 1);
+        s_last = (tk == cfg.nslabs - 1);
+        if (s_last) S.tickets[chunk] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int idx = threadIdx.x; idx < 3 * cbl * V; idx += blockDim.x) {
+            int cc = idx / (cbl * V), b2 = chunk * cbl * V + idx % (cbl * V);
             if (b2 >= B) continue;
             int o = cc * B + b2;
             double rho_new = sum_slabs<3>(S.partial, cc, b2, B, cfg.nslabs);
@@ -1189,22 +1269,38 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
     return DFDM_OK;
 }
 
-// z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
-static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
-                     size_t& used, MgParams mp) {
+// lane layout of the V-cycle kernels: V designs per thread
+static LaneCfg vec_base(int B, int V) {
+    LaneCfg cfg{};
+    int lanes = B / V, shift = 0;
+    while ((1 << shift) < lanes && shift < 5) ++shift;
+    cfg.shift = shift;
+    int cbl = 1 << shift;
+    cfg.nchunks = (lanes + cbl - 1) / cbl;
+    cfg.rstep = kThreads / cbl;
+    cfg.nslabs = 1;
+    return cfg;
+}
+
+template <int V>
+static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, int first, cudaStream_t st, size_t& used,
+                       MgParams mp) {
     const int nl = M.n_levels;
+    const LaneCfg vbase = vec_base(B, V);
+    static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1), up_tiles = tile_factor("DFDM_TILE_UP", 4);
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     for (int l = 0; l < nl; ++l) {
         MgMat A = mg_mat(P, M, w, l);
         if (l == 0) {
-            static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1);
-            LaneCfg c = rows_cfg(k_mg_down<double>, base, M.lv[l].n, down_tiles);
-            k_mg_down<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
+            LaneCfg c = rows_cfg(k_mg_down<double, V>, vbase, M.lv[l].n, down_tiles);
+            k_mg_down<double, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1],
+                                                                           w.S.n_active, mp);
             DFDM_LAUNCH_OK("k_mg_down");
             prof_mark(st, 3, used);
         } else {
-            LaneCfg c = rows_cfg(k_mg_down<mgf>, base, M.lv[l].n);
-            k_mg_down<mgf><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1], w.S.n_active, mp);
+            LaneCfg c = rows_cfg(k_mg_down<mgf, V>, vbase, M.lv[l].n);
+            k_mg_down<mgf, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1],
+                                                                        w.S.n_active, mp);
             DFDM_LAUNCH_OK("k_mg_down");
         }
     }
@@ -1221,20 +1317,26 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
         MgMat A = mg_mat(P, M, w, l);
         if (l == 0) {
             prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
-            static const int up_tiles = tile_factor("DFDM_TILE_UP", 4);
-            LaneCfg c = rows_cfg(k_mg_up<double>, base, A.n, up_tiles);
-            k_mg_up<double><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
-                                                                      1, first, mp);
+            LaneCfg c = rows_cfg(k_mg_up<double, V>, vbase, A.n, up_tiles);
+            k_mg_up<double, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.z[l + 1], w.mg.z[l],
+                                                                         w.S, 1, first, mp);
             DFDM_LAUNCH_OK("k_mg_up");
             prof_mark(st, 4, used);
         } else {
-            LaneCfg c = rows_cfg(k_mg_up<mgf>, base, A.n);
-            k_mg_up<mgf><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l], w.S,
-                                                                   0, first, mp);
+            LaneCfg c = rows_cfg(k_mg_up<mgf, V>, vbase, A.n);
+            k_mg_up<mgf, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l],
+                                                                      w.S, 0, first, mp);
             DFDM_LAUNCH_OK("k_mg_up");
         }
     }
     return DFDM_OK;
+}
+
+// z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
+static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
+                     size_t& used, MgParams mp) {
+    (void)base;
+    return (B % 2 == 0) ? mg_vcycle_v<2>(P, M, B, w, first, st, used, mp) : mg_vcycle_v<1>(P, M, B, w, first, st, used, mp);
 }
 
 static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
