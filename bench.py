@@ -329,7 +329,10 @@ def gpu_arm(args, rank, world, local_rank):
             "gpu_launches": launches}
     if solver == "pcg" and sum(prof_count) > 0:
         nc = plan.info.get("mg_n_coarse", 0)
-        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": 152.0 * nf * batch, "k_pcg_direction": (68.0 if plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi" else 80.0) * nf * batch,
+        is_mg = plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi"
+        # update: r in/out, Ap (+ 1/diag for Jacobi); direction: p in/out, x in/out, z (float) or r + 1/diag
+        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": (72.0 if is_mg else 80.0) * nf * batch,
+               "k_pcg_direction": (108.0 if is_mg else 128.0) * nf * batch,
                # single-precision V-cycle: K D^-1 (4 nnz), r in double (24 nf), t out (12 nf), coarse rhs out (12 nc)
                "k_mg_down[level 0]": (4.0 * nnz + 36.0 * nf + 12.0 * nc) * batch,
                # K (4 nnz), r (24 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)

@@ -56,7 +56,10 @@ struct PcgScalars {
     double* beta;
     double* bb;       // ||b||^2
     int32_t* frozen;  // [3][B] converged (or zero right-hand side): alpha forced to 0
-    int32_t* n_active;   // [0] columns not yet converged (live); [1] snapshot taken between iterations, read by the early exits
+    int32_t* n_active;   // [0] columns not yet converged (live); [1], [2] snapshots by iteration parity: kernels of iteration k
+                         // read [1 + par] (written during iteration k-1) and the direction kernel writes [1 + (par ^ 1)], so no
+                         // kernel ever reads a snapshot that a concurrently running CTA may be writing
+    int par;
     int32_t* tickets;    // [nchunks]
     double* partial;     // [nslabs][NV][B] scratch for block partials
 };
@@ -274,9 +277,16 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
 #define DFDM_SPMV_MINBLOCKS 4
 #endif
 #ifndef DFDM_UPD_MINBLOCKS
-#define DFDM_UPD_MINBLOCKS 3
+#define DFDM_UPD_MINBLOCKS 5
+#endif
+#ifndef DFDM_DIR_MINBLOCKS
+#define DFDM_DIR_MINBLOCKS 5
+#endif
+#ifndef DFDM_VEC_UNROLL
+#define DFDM_VEC_UNROLL 4
 #endif
 constexpr int kSpmvBatch = DFDM_SPMV_BATCH;
+constexpr int kVecUnroll = DFDM_VEC_UNROLL;
 
 // Ap = K p ; sigma = p . Ap ; alpha = rho / sigma
 // One thread per (row, design) carrying the three coordinates, so a matrix value is loaded once and
@@ -286,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
                                                                           const double* __restrict__ vals,
                                                                           const double* __restrict__ p, double* __restrict__ Ap,
                                                                           PcgScalars S) {
-    if (__ldcg(&S.n_active[1]) == 0) return;
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     LANE_SETUP();
     double v[3] = {0, 0, 0};
     if (live) {
@@ -345,27 +355,24 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
     }
 }
 
-// x += alpha p ; r -= alpha Ap ; rho' = r . (r/diag) ; rr = r.r ; beta = rho'/rho ; convergence
+// r -= alpha Ap ; rr = r.r ; Jacobi: rho' = r . (r/diag), beta = rho'/rho ; convergence
+// (x += alpha p lives in the direction kernel, which reads p anyway)
 __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(int nf, LaneCfg cfg, int B,
                                                                               const double* __restrict__ dinv,
-                                                                              const double* __restrict__ p,
-                                                                              const double* __restrict__ Ap, double* __restrict__ x,
-                                                                              double* __restrict__ r, PcgScalars S, double tol2, int mg) {
+                                                                              const double* __restrict__ Ap, double* __restrict__ r,
+                                                                              PcgScalars S, double tol2, int mg) {
     // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
-    if (__ldcg(&S.n_active[1]) == 0) return;
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     VEC_SETUP();
     double v[2] = {0, 0};
     if (live) {
         const double al = __ldcg(&S.alpha[c * B + b]);
-#pragma unroll 2
+#pragma unroll(kVecUnroll)
         for (int f = row0; f < nf; f += rstride) {
             size_t o = ((size_t)f * 3 + c) * B + b;
-            double di = dinv[(size_t)f * B + b];
-            double pc = p[o], ac = Ap[o], xc = x[o], rc = r[o];
-            x[o] = xc + al * pc;
-            rc -= al * ac;
+            double rc = r[o] - al * Ap[o];
             r[o] = rc;
-            v[0] += rc * rc * di;
+            if (!mg) v[0] += rc * rc * dinv[(size_t)f * B + b];
             v[1] += rc * rc;
         }
     }
@@ -397,20 +404,23 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
     }
 }
 
-// p = r / diag + beta p
-__global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+// x += alpha p ; p = z + beta p   (z = r / diag for Jacobi, the V-cycle output for multigrid)
+__global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                               const double* __restrict__ r, const float* __restrict__ z,
-                                                              double* __restrict__ p, PcgScalars S) {
-    if (__ldcg(&S.n_active[1]) == 0) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1] = __ldcg(&S.n_active[0]);   // p is dead once everything converged
+                                                              double* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd) {
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1 + (S.par ^ 1)] = __ldcg(&S.n_active[0]);
     VEC_SETUP();
     if (!live) return;
     const double be = __ldcg(&S.beta[c * B + b]);
-#pragma unroll 2
+    const double al = xupd ? __ldcg(&S.alpha[c * B + b]) : 0.0;
+#pragma unroll(kVecUnroll)
     for (int f = row0; f < nf; f += rstride) {
         size_t o = ((size_t)f * 3 + c) * B + b;
+        double pc = p[o];
+        if (xupd) x[o] += al * pc;
         double zc = z ? (double)z[o] : r[o] * dinv[(size_t)f * B + b];
-        p[o] = zc + be * p[o];
+        p[o] = zc + be * pc;
     }
 }
 
@@ -597,7 +607,7 @@ template <typename TB, int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
                                                       const mgf* __restrict__ t, const mgf* __restrict__ e_coarse,
                                                       mgf* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
-    if (__ldcg(&S.n_active[1]) == 0) return;
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     LANE_SETUP_V();
     double dsum[3][V];
 #pragma unroll
@@ -1294,23 +1304,23 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
         if (l == 0) {
             LaneCfg c = rows_cfg(k_mg_down<double, V>, vbase, M.lv[l].n, down_tiles);
             k_mg_down<double, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1],
-                                                                           w.S.n_active, mp);
+                                                                           w.S.n_active + w.S.par, mp);
             DFDM_LAUNCH_OK("k_mg_down");
             prof_mark(st, 3, used);
         } else {
             LaneCfg c = rows_cfg(k_mg_down<mgf, V>, vbase, M.lv[l].n);
             k_mg_down<mgf, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1],
-                                                                        w.S.n_active, mp);
+                                                                        w.S.n_active + w.S.par, mp);
             DFDM_LAUNCH_OK("k_mg_down");
         }
     }
     const MgLevelDev& C = M.lv[nl - 1];
     if (w.mg.Lf) {
-        k_mg_coarsest_solve<<<(C.n * 3 * B + 255) / 256, 256, 0, st>>>(C.n, B, w.mg.inv, w.mg.b[nl], w.mg.z[nl], w.S.n_active);
+        k_mg_coarsest_solve<<<(C.n * 3 * B + 255) / 256, 256, 0, st>>>(C.n, B, w.mg.inv, w.mg.b[nl], w.mg.z[nl], w.S.n_active + w.S.par);
         DFDM_LAUNCH_OK("k_mg_coarsest_solve");
     } else {
         MgMat A = mg_mat(P, M, w, nl);
-        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active, mp);
+        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active + w.S.par, mp);
         DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
     }
     for (int l = nl - 1; l >= 0; --l) {
@@ -1353,15 +1363,18 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
     double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
     int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : (mg ? 5 : 25);
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
-    DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, sizeof(int32_t), st));      // snapshot: non-zero
+    DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
+    w.S.par = 0;
     k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0);
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used0 = 0;
     if (mg) {
         int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0, mp);              // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
-        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.S);
+        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
+                                                                                   w.S, 0);
         DFDM_LAUNCH_OK("k_pcg_direction");
+        w.S.par ^= 1;
     }
     int it = 0;
     while (it < maxiter) {
@@ -1372,8 +1385,8 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
             k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
             DFDM_LAUNCH_OK("k_pcg_spmv");
             prof_mark(st, 0, used);
-            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.p, w.Ap, w.xs, w.r, w.S,
-                                                                                    rtol * rtol, mg ? 1 : 0);
+            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
+                                                                                    mg ? 1 : 0);
             DFDM_LAUNCH_OK("k_pcg_update");
             prof_mark(st, 1, used);
             if (mg) {
@@ -1382,9 +1395,10 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
                 prof_mark(st, -1, used);
             }
             k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r,
-                                                                                       mg ? w.mg.z[0] : nullptr, w.p, w.S);
+                                                                                       mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1);
             DFDM_LAUNCH_OK("k_pcg_direction");
             prof_mark(st, 2, used);
+            w.S.par ^= 1;
         }
         DFDM_CUDA_OK(cudaMemcpyAsync(host_flag, w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         DFDM_CUDA_OK(cudaStreamSynchronize(st));

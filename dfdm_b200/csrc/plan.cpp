@@ -350,6 +350,9 @@ static void build_pcg_order(Plan& P) {
         std::vector<int32_t> agg(sizes[l]);
         for (int i = 0; i < sizes[l]; ++i) agg[newid[l][i]] = newid[l + 1][aggs[l][i]];
         MgLevel L = build_level(sizes[l], rowptr, colidx, agg, sizes[l + 1]);
+        // hierarchical order: the members of an aggregate are consecutive rows (k_mg_down relies on it)
+        for (int m = 0; m < sizes[l]; ++m)
+            if (L.mem_idx[m] != m) set_error("internal: aggregate members are not contiguous");
         rowptr = L.rowptr;
         colidx = L.colidx;
         P.mg.push_back(std::move(L));

@@ -210,8 +210,8 @@ DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_
  * ms / count are indexed by DFDM_PROF_* (8 entries each).  Not thread safe; meant for bench.py.
  */
 #define DFDM_PROF_SPMV 0       /* k_pcg_spmv:      Ap = K p, p.Ap            algorithmic bytes 8 nnz + 48 n_free per design */
-#define DFDM_PROF_UPDATE 1     /* k_pcg_update:    x, r update, r.z, r.r     152 n_free per design */
-#define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: p = z + beta p            80 n_free per design */
+#define DFDM_PROF_UPDATE 1     /* k_pcg_update:    r -= alpha Ap, r.r (r.z)  72 n_free (multigrid) / 80 n_free (Jacobi) per design */
+#define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: x += alpha p, p = z + beta p   108 n_free (multigrid) / 128 n_free (Jacobi) */
 #define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   8 nnz + 48 n_free + 24 n_coarse */
 #define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          8 nnz + 80 n_free + 24 n_coarse */
 #define DFDM_PROF_MG_COARSE 5  /* all kernels below the finest level, per V-cycle */

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for so in build/variants/*.so; do
   name=$(basename $so .so)
-  DFDM_B200_LIB=$PWD/$so python bench.py --steps 1 --warmup 1 --no-cpu --pcg-maxiter 100 > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
+  DFDM_B200_LIB=$PWD/$so python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
   python - <<PY
 import json
 try:
