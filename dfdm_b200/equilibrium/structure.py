@@ -5,11 +5,36 @@ Same lazy properties as the reference; in addition ``plan`` is the compiled topo
 consume.  ``connectivity`` is materialised as a dense array only when somebody asks for it — the
 kernels never do (a 66 564-node grid would need 35 GB).
 """
+from collections import OrderedDict
+
 import numpy as np
 
 from dfdm_b200.engine import Plan
 
-__all__ = ["EquilibriumStructure"]
+__all__ = ["EquilibriumStructure", "cached_plan"]
+
+_PLAN_CACHE = OrderedDict()
+_PLAN_CACHE_SIZE = 16
+
+
+def cached_plan(n, edges, is_fixed):
+    """
+    Plans are pure functions of the topology, and the reference rebuilds its model in every ``fdm()``,
+    ``minimize()`` and example loop (fdm.py:15, optimization.py:50): keep the last few compiled plans,
+    keyed by the exact bytes of ``(n, edges, is_fixed)``.
+    """
+    edges = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
+    is_fixed = np.ascontiguousarray(np.asarray(is_fixed).astype(np.uint8))
+    key = (int(n), edges.tobytes(), is_fixed.tobytes())
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = Plan(n, edges, is_fixed)
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return plan
 
 
 class EquilibriumStructure:
@@ -52,7 +77,7 @@ class EquilibriumStructure:
         if self._plan is None:
             network = self.network
             is_fixed = np.asarray([1 if network.node_attribute(key, "is_support") else 0 for key in network.nodes()], dtype=np.uint8)
-            self._plan = Plan(len(is_fixed), self.edges, is_fixed)
+            self._plan = cached_plan(len(is_fixed), self.edges, is_fixed)
         return self._plan
 
     @property

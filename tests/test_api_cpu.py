@@ -208,3 +208,15 @@ def test_shard_bounds_cover_the_batch_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == batch
             assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_plans_are_cached_by_topology():
+    from dfdm_b200.equilibrium.structure import cached_plan
+    a = EquilibriumModel(CASES["dome"]["network"])
+    b = EquilibriumModel(CASES["dome"]["network"].copy())
+    assert a.plan is b.plan
+    other = CASES["dome"]["network"].copy()
+    other.node_support(40)
+    assert EquilibriumModel(other).plan is not a.plan
+    edges, is_fixed, _, _ = case_arrays(CASES["pillow"])
+    assert cached_plan(len(is_fixed), edges, is_fixed) is cached_plan(len(is_fixed), edges.copy(), is_fixed.copy())

@@ -201,3 +201,46 @@ def test_large_grid_properties_pcg():
     assert np.allclose(res.sum(axis=1), loads.sum(axis=0)[None, :], atol=1e-9 * np.abs(res).max())
     f, a = _lib.last_pcg_iterations()
     assert 0 < f < 5000 and 0 < a < 5000
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "multigrid"])
+@pytest.mark.parametrize("batch", [1, 5, 6])
+def test_pcg_preconditioners_agree_with_sparse_oracle(precond, batch):
+    """Odd batches take the one-design-per-thread V-cycle kernels, even ones the two-design kernels; B = 1 folds rows into warps."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(40)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.info["mg_levels"] >= 3
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", pcg_precond=precond)
+    q = W.sample_q(q0, batch, seed=11, spread=0.6, relative=True)
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    out = ev.loss_and_grad(prog, q, outputs=("xyz",))
+    assert np.all(out["status"].cpu().numpy() == 0)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    for b in sorted({0, batch - 1}):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.1)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+    f, a = _lib.last_pcg_iterations()
+    if precond == "multigrid":
+        assert f <= 60 and a <= 60          # the V-cycle cuts the iteration count by an order of magnitude
+    else:
+        assert f > 100
+
+
+def test_pcg_flags_an_indefinite_operator_instead_of_returning_garbage():
+    """Mixed-sign force densities on the CG path: not converged is reported per design (the direct path solves them)."""
+    case = CASES["mixed_sign"]
+    edges, is_fixed, xyz, loads = case_arrays(case)
+    plan = Plan(len(is_fixed), edges, is_fixed)
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", pcg_maxiter=200)
+    good = -np.abs(case["q"])
+    out = ev.forward(np.stack([good, case["q"]]))
+    status = out["status"].cpu().numpy()
+    assert status[0] == _lib.STATUS_OK
+    assert status[1] in (_lib.STATUS_NOT_CONVERGED, _lib.STATUS_NONFINITE)
+    direct = Evaluator(plan, loads, xyz[plan.fixed], solver="direct").forward(case["q"])
+    assert int(direct["status"].cpu()[0]) == _lib.STATUS_OK
