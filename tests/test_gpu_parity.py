@@ -231,16 +231,21 @@ def test_pcg_preconditioners_agree_with_sparse_oracle(precond, batch):
         assert f > 100
 
 
-def test_pcg_flags_an_indefinite_operator_instead_of_returning_garbage():
-    """Mixed-sign force densities on the CG path: not converged is reported per design (the direct path solves them)."""
+def test_pcg_on_an_indefinite_operator_is_either_right_or_flagged():
+    """Mixed-sign force densities on the CG path: a design is reported as not converged, or its answer is the reference's."""
     case = CASES["mixed_sign"]
+    g = np.load(os.path.join(GOLDEN, "mixed_sign.npz"))
     edges, is_fixed, xyz, loads = case_arrays(case)
     plan = Plan(len(is_fixed), edges, is_fixed)
-    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", pcg_maxiter=200)
-    good = -np.abs(case["q"])
-    out = ev.forward(np.stack([good, case["q"]]))
-    status = out["status"].cpu().numpy()
-    assert status[0] == _lib.STATUS_OK
-    assert status[1] in (_lib.STATUS_NOT_CONVERGED, _lib.STATUS_NONFINITE)
     direct = Evaluator(plan, loads, xyz[plan.fixed], solver="direct").forward(case["q"])
     assert int(direct["status"].cpu()[0]) == _lib.STATUS_OK
+    assert _rel(direct["xyz"].cpu().numpy()[0], g["xyz"]) < TOL_X
+    for precond in ("jacobi", "multigrid"):
+        ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", pcg_maxiter=300, pcg_precond=precond)
+        out = ev.forward(np.stack([-np.abs(case["q"]), case["q"]]))
+        status = out["status"].cpu().numpy()
+        assert status[0] == _lib.STATUS_OK
+        if status[1] == _lib.STATUS_OK:
+            assert _rel(out["xyz"].cpu().numpy()[1], g["xyz"]) < 1e-7
+        else:
+            assert status[1] in (_lib.STATUS_NOT_CONVERGED, _lib.STATUS_NONFINITE)
