@@ -230,7 +230,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over)
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels)
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -319,7 +319,7 @@ def gpu_arm(args, rank, world, local_rank):
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
-                       "preconditioner": ("multigrid V(1,1), %d levels" % (plan.info.get("mg_levels", 0) + 1)) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
+                       "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 2))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients)" % world,
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
                        "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
@@ -392,6 +392,7 @@ def main():
     ap.add_argument("--precond", default="auto", choices=["auto", "jacobi", "multigrid"])
     ap.add_argument("--mg-omega", type=float, default=0.0)
     ap.add_argument("--mg-over", type=float, default=0.0)
+    ap.add_argument("--mg-w-levels", type=int, default=0, help="coarse levels visited twice per cycle (0: default 2, -1: V-cycle)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

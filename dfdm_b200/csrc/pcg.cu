@@ -453,7 +453,8 @@ struct MgMat {                 // one level's operator (level 0: the plan's CSR 
 };
 
 constexpr double kMgOmegaDefault = 0.8;
-constexpr double kMgOverDefault = 1.7;
+constexpr double kMgOverDefault = 1.7;   // V-cycle
+constexpr double kMgOverW = 1.3;         // W-cycle: nested scalings multiply, so stay below sqrt(2) (1.5 is faster on grids, 1.7 diverges)
 struct MgParams { float omega, over; };
 
 // level 0: single-precision copies of K, K D^-1 and 1/diag from the assembled double-precision operator
@@ -708,6 +709,39 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
             if (!S.frozen[o] || first) S.rho[o] = rho_new;
         }
     }
+}
+
+// W-cycle helpers on a coarse level: r2 = rhs - A x, and out += z2
+template <int V>
+__global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, int B, const mgf* __restrict__ rhs,
+                                                         const mgf* __restrict__ x, mgf* __restrict__ r2,
+                                                         const int32_t* __restrict__ n_active) {
+    if (__ldcg(&n_active[1]) == 0) return;
+    LANE_SETUP_V();
+    if (!live) return;
+    const size_t sB = (size_t)B;
+    TILE_ROWS(f, A.n) {
+        int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+        Vf<V> acc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[c].v[v] = 0.0f;
+        mg_row<V, mgf>(A.ell_col, A.ell_w, f, k0, len, A.vals + b, x + b, sB, acc);
+        size_t o = (size_t)f * 3 * sB + b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Vf<V> bc = ldv<V>(rhs + o + c * sB);
+#pragma unroll
+            for (int v = 0; v < V; ++v) bc.v[v] -= acc[c].v[v];
+            stv<V>(r2 + o + c * sB, bc);
+        }
+    }
+}
+
+__global__ void k_mg_add(int64_t count, mgf* __restrict__ out, const mgf* __restrict__ z2, const int32_t* __restrict__ n_active) {
+    if (__ldcg(&n_active[1]) == 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) out[i] += z2[i];
 }
 
 // coarsest level: dense LDL^T per design in double precision, interleaved storage Lf[(i(i+1)/2 + j)][B]
@@ -1086,6 +1120,8 @@ struct MgBuffers {
     mgf* b[kMaxMgLevels + 1] = {nullptr};              // level 0: the CG residual itself (double), not stored here
     mgf* t[kMaxMgLevels + 1] = {nullptr};
     mgf* z[kMaxMgLevels + 1] = {nullptr};
+    mgf* r2[kMaxMgLevels + 1] = {nullptr};             // W-cycle: residual after the first visit and the second correction
+    mgf* z2[kMaxMgLevels + 1] = {nullptr};
     double* Lf = nullptr;
     double* inv_work = nullptr;
     mgf* inv = nullptr;
@@ -1094,7 +1130,7 @@ struct MgBuffers {
 
 struct PcgBuffers {
     MgBuffers mg;
-    double *qT, *vals, *dinv, *xs, *r, *p, *Ap;
+    double *qT, *vals, *dinv, *xs, *r, *p, *Ap, *rhs_keep;
     double *X, *R, *U, *L, *F, *Xb, *Rb, *Ub, *dqT;
     double *cX, *cR, *cU, *cL, *cF;
     double *lp_partial, *pn, *pe, *lpbar, *net_loss;
@@ -1118,6 +1154,8 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
             w.mg.b[l] = bump.take<mgf>(nl * 3 * B);
             w.mg.t[l] = bump.take<mgf>(nl * 3 * B);
             w.mg.z[l] = bump.take<mgf>(nl * 3 * B);
+            w.mg.r2[l] = bump.take<mgf>(nl * 3 * B);
+            w.mg.z2[l] = bump.take<mgf>(nl * 3 * B);
         }
         int64_t nc = mg_n[mg_levels - 1];
         if (nc <= kCoarsestDense) {
@@ -1135,6 +1173,7 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
     w.r = bump.take<double>(nf * 3 * B);
     w.p = bump.take<double>(nf * 3 * B);
     w.Ap = bump.take<double>(nf * 3 * B);
+    w.rhs_keep = bump.take<double>(mg_levels > 0 ? nf * 3 * B : 0);
     w.X = bump.take<double>(n * 3 * B);
     w.R = bump.take<double>(n * 3 * B);
     w.U = bump.take<double>(E * 3 * B);
@@ -1292,67 +1331,137 @@ static LaneCfg vec_base(int B, int V) {
     return cfg;
 }
 
+struct MgCtx {
+    const PlanDev* P;
+    const MgDev* M;
+    PcgBuffers* w;
+    int B;
+    cudaStream_t st;
+    MgParams mp;
+    LaneCfg vbase;
+    int w_levels;          // coarse levels 1 .. w_levels are visited twice per visit of their parent (W-cycle)
+};
+
+// out = M_l rhs on coarse level l (1 <= l <= n_levels): exact on the coarsest level, one (V) or two (W) cycles above it
+template <int V>
+static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out);
+
+template <int V>
+static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
+    const MgDev& M = *c.M;
+    PcgBuffers& w = *c.w;
+    MgMat A = mg_mat(*c.P, M, w, l);
+    LaneCfg cd = rows_cfg(k_mg_down<mgf, V>, c.vbase, M.lv[l].n);
+    k_mg_down<mgf, V><<<cd.nchunks * cd.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cd, c.B, rhs, w.mg.t[l], w.mg.b[l + 1],
+                                                                      w.S.n_active + w.S.par, c.mp);
+    DFDM_LAUNCH_OK("k_mg_down");
+    int rc = mg_solve_level<V>(c, l + 1, w.mg.b[l + 1], w.mg.z[l + 1]);
+    if (rc) return rc;
+    LaneCfg cu = rows_cfg(k_mg_up<mgf, V>, c.vbase, A.n);
+    k_mg_up<mgf, V><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S, 0, 0,
+                                                                    c.mp);
+    DFDM_LAUNCH_OK("k_mg_up");
+    return DFDM_OK;
+}
+
+template <int V>
+static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
+    const MgDev& M = *c.M;
+    PcgBuffers& w = *c.w;
+    const int nl = M.n_levels;
+    if (l == nl) {
+        const MgLevelDev& C = M.lv[nl - 1];
+        if (w.mg.Lf) {
+            k_mg_coarsest_solve<<<(C.n * 3 * c.B + 255) / 256, 256, 0, c.st>>>(C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par);
+            DFDM_LAUNCH_OK("k_mg_coarsest_solve");
+        } else {
+            MgMat A = mg_mat(*c.P, M, w, nl);
+            k_mg_coarsest_jacobi<<<c.B, 256, 0, c.st>>>(A, c.B, 24, rhs, out, w.mg.tmp, w.S.n_active + w.S.par, c.mp);
+            DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
+        }
+        return DFDM_OK;
+    }
+    int rc = mg_cycle_level<V>(c, l, rhs, out);
+    if (rc) return rc;
+    if (l <= c.w_levels) {
+        // second visit on the residual of the first: out += M_l (rhs - A_l out)
+        MgMat A = mg_mat(*c.P, M, w, l);
+        LaneCfg cr = rows_cfg(k_mg_resid<V>, c.vbase, A.n);
+        k_mg_resid<V><<<cr.nchunks * cr.nslabs, kThreads, 0, c.st>>>(A, cr, c.B, rhs, out, w.mg.r2[l], w.S.n_active + w.S.par);
+        DFDM_LAUNCH_OK("k_mg_resid");
+        rc = mg_cycle_level<V>(c, l, w.mg.r2[l], w.mg.z2[l]);
+        if (rc) return rc;
+        int64_t count = (int64_t)A.n * 3 * c.B;
+        int grid = (int)std::min<int64_t>((count + 255) / 256, 148 * 8);
+        k_mg_add<<<grid, 256, 0, c.st>>>(count, out, w.mg.z2[l], w.S.n_active + w.S.par);
+        DFDM_LAUNCH_OK("k_mg_add");
+    }
+    return DFDM_OK;
+}
+
 template <int V>
 static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, int first, cudaStream_t st, size_t& used,
-                       MgParams mp) {
-    const int nl = M.n_levels;
-    const LaneCfg vbase = vec_base(B, V);
+                       MgParams mp, int w_levels) {
     static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1), up_tiles = tile_factor("DFDM_TILE_UP", 4);
+    MgCtx c{&P, &M, &w, B, st, mp, vec_base(B, V), w_levels};
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
-    for (int l = 0; l < nl; ++l) {
-        MgMat A = mg_mat(P, M, w, l);
-        if (l == 0) {
-            LaneCfg c = rows_cfg(k_mg_down<double, V>, vbase, M.lv[l].n, down_tiles);
-            k_mg_down<double, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.b[l + 1],
-                                                                           w.S.n_active + w.S.par, mp);
-            DFDM_LAUNCH_OK("k_mg_down");
-            prof_mark(st, 3, used);
-        } else {
-            LaneCfg c = rows_cfg(k_mg_down<mgf, V>, vbase, M.lv[l].n);
-            k_mg_down<mgf, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.b[l + 1],
-                                                                        w.S.n_active + w.S.par, mp);
-            DFDM_LAUNCH_OK("k_mg_down");
-        }
-    }
-    const MgLevelDev& C = M.lv[nl - 1];
-    if (w.mg.Lf) {
-        k_mg_coarsest_solve<<<(C.n * 3 * B + 255) / 256, 256, 0, st>>>(C.n, B, w.mg.inv, w.mg.b[nl], w.mg.z[nl], w.S.n_active + w.S.par);
-        DFDM_LAUNCH_OK("k_mg_coarsest_solve");
-    } else {
-        MgMat A = mg_mat(P, M, w, nl);
-        k_mg_coarsest_jacobi<<<B, 256, 0, st>>>(A, B, 24, w.mg.b[nl], w.mg.z[nl], w.mg.tmp, w.S.n_active + w.S.par, mp);
-        DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
-    }
-    for (int l = nl - 1; l >= 0; --l) {
-        MgMat A = mg_mat(P, M, w, l);
-        if (l == 0) {
-            prof_mark(st, 5, used);          // everything below the finest level, per V-cycle
-            LaneCfg c = rows_cfg(k_mg_up<double, V>, vbase, A.n, up_tiles);
-            k_mg_up<double, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.r, w.mg.t[l], w.mg.z[l + 1], w.mg.z[l],
-                                                                         w.S, 1, first, mp);
-            DFDM_LAUNCH_OK("k_mg_up");
-            prof_mark(st, 4, used);
-        } else {
-            LaneCfg c = rows_cfg(k_mg_up<mgf, V>, vbase, A.n);
-            k_mg_up<mgf, V><<<c.nchunks * c.nslabs, kThreads, 0, st>>>(A, M.lv[l], c, B, w.mg.b[l], w.mg.t[l], w.mg.z[l + 1], w.mg.z[l],
-                                                                      w.S, 0, first, mp);
-            DFDM_LAUNCH_OK("k_mg_up");
-        }
-    }
+    MgMat A = mg_mat(P, M, w, 0);
+    LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
+    k_mg_down<double, V><<<cd.nchunks * cd.nslabs, kThreads, 0, st>>>(A, M.lv[0], cd, B, w.r, w.mg.t[0], w.mg.b[1],
+                                                                     w.S.n_active + w.S.par, mp);
+    DFDM_LAUNCH_OK("k_mg_down");
+    prof_mark(st, 3, used);
+    int rc = mg_solve_level<V>(c, 1, w.mg.b[1], w.mg.z[1]);
+    if (rc) return rc;
+    prof_mark(st, 5, used);                              // everything below the finest level, per cycle
+    LaneCfg cu = rows_cfg(k_mg_up<double, V>, c.vbase, A.n, up_tiles);
+    k_mg_up<double, V><<<cu.nchunks * cu.nslabs, kThreads, 0, st>>>(A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0], w.S, 1,
+                                                                   first, mp);
+    DFDM_LAUNCH_OK("k_mg_up");
+    prof_mark(st, 4, used);
     return DFDM_OK;
 }
 
 // z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
 static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
-                     size_t& used, MgParams mp) {
+                     size_t& used, MgParams mp, int w_levels) {
     (void)base;
-    return (B % 2 == 0) ? mg_vcycle_v<2>(P, M, B, w, first, st, used, mp) : mg_vcycle_v<1>(P, M, B, w, first, st, used, mp);
+    return (B % 2 == 0) ? mg_vcycle_v<2>(P, M, B, w, first, st, used, mp, w_levels)
+                        : mg_vcycle_v<1>(P, M, B, w, first, st, used, mp, w_levels);
 }
 
+static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
+                          cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap);
+
+// Solve K x = r for all designs.  The multigrid preconditioner is tried first with a generous iteration cap; should it
+// fail to converge (an over-corrected cycle can lose definiteness on unusual networks), the right-hand side is restored
+// and the solve is repeated with the Jacobi preconditioner, which is definite whenever K is.
 static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
                      cudaStream_t st, int32_t* host_flag, int* iters_out) {
     const bool mg = M != nullptr && M->n_levels > 0;
-    MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault), (float)(opt.mg_over > 0 ? opt.mg_over : kMgOverDefault)};
+    if (!mg) return pcg_solve_once(P, nullptr, base, B, w, opt, st, host_flag, iters_out, 0);
+    const size_t bytes = sizeof(double) * (size_t)P.nf * 3 * B;
+    DFDM_CUDA_OK(cudaMemcpyAsync(w.rhs_keep, w.r, bytes, cudaMemcpyDeviceToDevice, st));
+    const int cap = opt.pcg_maxiter > 0 ? std::min(opt.pcg_maxiter, 400) : 400;
+    int rc = pcg_solve_once(P, M, base, B, w, opt, st, host_flag, iters_out, cap);
+    if (rc || *host_flag == 0) return rc;
+    if (opt.pcg_maxiter > 0 && opt.pcg_maxiter <= cap) return DFDM_OK;      // the caller asked for a short run
+    DFDM_CUDA_OK(cudaMemcpyAsync(w.r, w.rhs_keep, bytes, cudaMemcpyDeviceToDevice, st));
+    int extra = 0;
+    rc = pcg_solve_once(P, nullptr, base, B, w, opt, st, host_flag, &extra, 0);
+    *iters_out += extra;
+    return rc;
+}
+
+static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
+                          cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap) {
+    const bool mg = M != nullptr && M->n_levels > 0;
+    // cycle shape: coarse levels 1 .. w_levels are visited twice (W-cycle); deeper levels once.  Plain aggregation gains
+    // most from revisiting the first coarse levels, and the tiny ones below are latency bound, so the default is 2.
+    int w_levels = opt.mg_w_levels < 0 ? 0 : (opt.mg_w_levels > 0 ? opt.mg_w_levels : 2);
+    if (mg) w_levels = std::min(w_levels, std::max(0, M->n_levels - 1));
+    MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault),
+                (float)(opt.mg_over > 0 ? opt.mg_over : (w_levels > 0 ? kMgOverW : kMgOverDefault))};
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
     static const int spmv_tiles = tile_factor("DFDM_TILE_SPMV", 4);
     const LaneCfg cfg_spmv = rows_cfg(k_pcg_spmv, base, P.nf, spmv_tiles);
@@ -1360,6 +1469,7 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
     const LaneCfg cfg_dir = one_wave(k_pcg_direction, base, P.nf, kVecThreads);
     int grid = cfg.nchunks * cfg.nslabs;
     int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
+    if (iter_cap > 0) maxiter = std::min(maxiter, iter_cap);
     double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
     int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : (mg ? 5 : 25);
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
@@ -1369,7 +1479,7 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used0 = 0;
     if (mg) {
-        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0, mp);              // z = M r, rho = r.z, beta = 0
+        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0, mp, w_levels);              // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
         k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
                                                                                    w.S, 0);
@@ -1390,7 +1500,7 @@ static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int 
             DFDM_LAUNCH_OK("k_pcg_update");
             prof_mark(st, 1, used);
             if (mg) {
-                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used, mp);
+                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used, mp, w_levels);
                 if (rc) return rc;
                 prof_mark(st, -1, used);
             }

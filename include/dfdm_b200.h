@@ -64,7 +64,9 @@ typedef struct dfdm_options {
     int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 (Jacobi) / 5 (multigrid) */
     int32_t pcg_precond;     /* DFDM_PRECOND_*; AUTO = aggregation multigrid V-cycle when the plan has coarse levels */
     double mg_omega;         /* damping of the Jacobi smoother; <= 0: default 0.8 */
-    double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects); <= 0: default 1.5 */
+    double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects); <= 0: 1.5 (W) / 1.7 (V) */
+    int32_t mg_w_levels;     /* coarse levels 1..k are visited twice per cycle (W-cycle); 0: default 2; < 0: plain V-cycle */
+    int32_t reserved;
 } dfdm_options;
 
 /* preconditioner of the PCG path */

@@ -249,3 +249,16 @@ def test_pcg_on_an_indefinite_operator_is_either_right_or_flagged():
             assert _rel(out["xyz"].cpu().numpy()[1], g["xyz"]) < 1e-7
         else:
             assert status[1] in (_lib.STATUS_NOT_CONVERGED, _lib.STATUS_NONFINITE)
+
+
+def test_overcorrected_cycle_falls_back_to_jacobi_instead_of_failing():
+    """A W-cycle with an absurd over-correction is not a definite preconditioner; the solve must still come back right."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(40)
+    plan = Plan(len(fixed), edges, fixed)
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", mg_over=1.98, mg_w_levels=3)
+    q = W.sample_q(q0, 4, seed=3, spread=0.2, relative=True)
+    out = ev.forward(q, outputs=("xyz",))
+    assert np.all(out["status"].cpu().numpy() == 0)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    assert _rel(out["xyz"].cpu().numpy()[2], sm(q[2]).xyz) < TOL_X
