@@ -262,3 +262,31 @@ def test_overcorrected_cycle_falls_back_to_jacobi_instead_of_failing():
     assert np.all(out["status"].cpu().numpy() == 0)
     sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
     assert _rel(out["xyz"].cpu().numpy()[2], sm(q[2]).xyz) < TOL_X
+
+
+@pytest.mark.parametrize("name", ["dome", "monkey_saddle", "pringle"])
+def test_multigrid_pcg_matches_direct_path_on_unstructured_networks(name):
+    """Medium networks of the example families forced onto the CG path: same answers as the shared-memory factorisation."""
+    from dfdm_b200 import workloads as W
+    if name == "dome":
+        net = W.dome(num_sides=24, num_rings=30, offset_distance=0.012)
+    elif name == "monkey_saddle":
+        net, _ = W.monkey_saddle(n=10)
+    else:
+        net = W.pringle(num_u=40, num_v=21)
+    edges, is_fixed, xyz, loads, q0 = W.network_arrays(net)
+    plan = Plan(len(is_fixed), edges, is_fixed)
+    assert plan.info["mg_levels"] >= 2
+    rng = np.random.default_rng(8)
+    q = q0[None, :] * (1.0 + 0.6 * (rng.random((6, len(q0))) - 0.5))
+    goals = [("NodePoint", int(i), 0, 1.0, list(xyz[i] + [0.0, 0.0, 0.3])) for i in plan.free[::7]]
+    goals += [("EdgeLength", e, 0, 0.5, [0.9 * float(np.linalg.norm(xyz[edges[e, 1]] - xyz[edges[e, 0]]))]) for e in range(0, len(edges), 5)]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.01)
+    ref = Evaluator(plan, loads, xyz[plan.fixed], solver="direct").loss_and_grad(prog, q, outputs=("xyz",))
+    out = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg").loss_and_grad(prog, q, outputs=("xyz",))
+    assert np.all(ref["status"].cpu().numpy() == 0) and np.all(out["status"].cpu().numpy() == 0)
+    assert _rel(out["xyz"].cpu().numpy(), ref["xyz"].cpu().numpy()) < TOL_X
+    assert _rel(out["loss"].cpu().numpy(), ref["loss"].cpu().numpy()) < 1e-9
+    assert _rel(out["dq"].cpu().numpy(), ref["dq"].cpu().numpy()) < TOL_G
+    f, a = _lib.last_pcg_iterations()
+    assert f <= 120 and a <= 120
