@@ -604,10 +604,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, 
 }
 
 // up pass of a level: z = smoothed, coarse-corrected solution.  With `dots` (level 0) also rho' = r . z -> beta.
-template <typename TB, int V>
+template <typename TB, int V, bool ACC>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
                                                       const mgf* __restrict__ t, const mgf* __restrict__ e_coarse,
                                                       mgf* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
+    // ACC: the W-cycle's second visit adds its correction to the first one (already in z) instead of in a separate pass
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     LANE_SETUP_V();
     double dsum[3][V];
@@ -664,6 +665,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
                     zc.v[v] = xn + w * (bc.v[v] - mp.omega * tc.v[v] - mp.over * sacc[c].v[v]);
                     dsum[c][v] += (double)bc.v[v] * (double)zc.v[v];
                 }
+                if (ACC) {
+                    Vf<V> prev = ldv<V>(z + o + c * sB);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) zc.v[v] += prev.v[v];
+                }
                 stv<V>(z + o + c * sB, zc);
             }
         }
@@ -711,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
     }
 }
 
-// W-cycle helpers on a coarse level: r2 = rhs - A x, and out += z2
+// W-cycle helper on a coarse level: r2 = rhs - A x
 template <int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, int B, const mgf* __restrict__ rhs,
                                                          const mgf* __restrict__ x, mgf* __restrict__ r2,
@@ -737,11 +743,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, 
             stv<V>(r2 + o + c * sB, bc);
         }
     }
-}
-
-__global__ void k_mg_add(int64_t count, mgf* __restrict__ out, const mgf* __restrict__ z2, const int32_t* __restrict__ n_active) {
-    if (__ldcg(&n_active[1]) == 0) return;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) out[i] += z2[i];
 }
 
 // coarsest level: dense LDL^T per design in double precision, interleaved storage Lf[(i(i+1)/2 + j)][B]
@@ -1120,8 +1121,7 @@ struct MgBuffers {
     mgf* b[kMaxMgLevels + 1] = {nullptr};              // level 0: the CG residual itself (double), not stored here
     mgf* t[kMaxMgLevels + 1] = {nullptr};
     mgf* z[kMaxMgLevels + 1] = {nullptr};
-    mgf* r2[kMaxMgLevels + 1] = {nullptr};             // W-cycle: residual after the first visit and the second correction
-    mgf* z2[kMaxMgLevels + 1] = {nullptr};
+    mgf* r2[kMaxMgLevels + 1] = {nullptr};             // W-cycle: residual after the first visit
     double* Lf = nullptr;
     double* inv_work = nullptr;
     mgf* inv = nullptr;
@@ -1155,7 +1155,6 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
             w.mg.t[l] = bump.take<mgf>(nl * 3 * B);
             w.mg.z[l] = bump.take<mgf>(nl * 3 * B);
             w.mg.r2[l] = bump.take<mgf>(nl * 3 * B);
-            w.mg.z2[l] = bump.take<mgf>(nl * 3 * B);
         }
         int64_t nc = mg_n[mg_levels - 1];
         if (nc <= kCoarsestDense) {
@@ -1347,7 +1346,7 @@ template <int V>
 static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out);
 
 template <int V>
-static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
+static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out, const mgf* acc) {
     const MgDev& M = *c.M;
     PcgBuffers& w = *c.w;
     MgMat A = mg_mat(*c.P, M, w, l);
@@ -1357,9 +1356,15 @@ static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
     DFDM_LAUNCH_OK("k_mg_down");
     int rc = mg_solve_level<V>(c, l + 1, w.mg.b[l + 1], w.mg.z[l + 1]);
     if (rc) return rc;
-    LaneCfg cu = rows_cfg(k_mg_up<mgf, V>, c.vbase, A.n);
-    k_mg_up<mgf, V><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S, 0, 0,
-                                                                    c.mp);
+    if (acc) {
+        LaneCfg cu = rows_cfg(k_mg_up<mgf, V, true>, c.vbase, A.n);
+        k_mg_up<mgf, V, true><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
+                                                                              0, 0, c.mp);
+    } else {
+        LaneCfg cu = rows_cfg(k_mg_up<mgf, V, false>, c.vbase, A.n);
+        k_mg_up<mgf, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
+                                                                               0, 0, c.mp);
+    }
     DFDM_LAUNCH_OK("k_mg_up");
     return DFDM_OK;
 }
@@ -1381,7 +1386,7 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
         }
         return DFDM_OK;
     }
-    int rc = mg_cycle_level<V>(c, l, rhs, out);
+    int rc = mg_cycle_level<V>(c, l, rhs, out, nullptr);
     if (rc) return rc;
     if (l <= c.w_levels) {
         // second visit on the residual of the first: out += M_l (rhs - A_l out)
@@ -1389,12 +1394,8 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
         LaneCfg cr = rows_cfg(k_mg_resid<V>, c.vbase, A.n);
         k_mg_resid<V><<<cr.nchunks * cr.nslabs, kThreads, 0, c.st>>>(A, cr, c.B, rhs, out, w.mg.r2[l], w.S.n_active + w.S.par);
         DFDM_LAUNCH_OK("k_mg_resid");
-        rc = mg_cycle_level<V>(c, l, w.mg.r2[l], w.mg.z2[l]);
+        rc = mg_cycle_level<V>(c, l, w.mg.r2[l], out, out);
         if (rc) return rc;
-        int64_t count = (int64_t)A.n * 3 * c.B;
-        int grid = (int)std::min<int64_t>((count + 255) / 256, 148 * 8);
-        k_mg_add<<<grid, 256, 0, c.st>>>(count, out, w.mg.z2[l], w.S.n_active + w.S.par);
-        DFDM_LAUNCH_OK("k_mg_add");
     }
     return DFDM_OK;
 }
@@ -1414,9 +1415,9 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     int rc = mg_solve_level<V>(c, 1, w.mg.b[1], w.mg.z[1]);
     if (rc) return rc;
     prof_mark(st, 5, used);                              // everything below the finest level, per cycle
-    LaneCfg cu = rows_cfg(k_mg_up<double, V>, c.vbase, A.n, up_tiles);
-    k_mg_up<double, V><<<cu.nchunks * cu.nslabs, kThreads, 0, st>>>(A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0], w.S, 1,
-                                                                   first, mp);
+    LaneCfg cu = rows_cfg(k_mg_up<double, V, false>, c.vbase, A.n, up_tiles);
+    k_mg_up<double, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, st>>>(A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0],
+                                                                          w.S, 1, first, mp);
     DFDM_LAUNCH_OK("k_mg_up");
     prof_mark(st, 4, used);
     return DFDM_OK;
