@@ -220,3 +220,15 @@ def test_plans_are_cached_by_topology():
     assert EquilibriumModel(other).plan is not a.plan
     edges, is_fixed, _, _ = case_arrays(CASES["pillow"])
     assert cached_plan(len(is_fixed), edges, is_fixed) is cached_plan(len(is_fixed), edges.copy(), is_fixed.copy())
+
+
+def test_reference_import_paths_resolve_after_compat_install():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import dfdm_b200.compat as c; c.install(); "
+            "from dfdm.equilibrium import fdm, constrained_fdm, EquilibriumModel; from dfdm.datastructures import FDNetwork; "
+            "from dfdm.goals import NodeLineGoal, EdgeLengthGoal, NetworkLoadPathGoal; from dfdm.losses import Loss, SquaredError, L2Regularizer; "
+            "from dfdm.constraints import NetworkEdgesLengthConstraint, NodeCurvatureConstraint; "
+            "from dfdm.optimization import SLSQP, BFGS, TrustRegionConstrained, OptimizationRecorder; print('ok')") % os.path.join(os.path.dirname(__file__), "..")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

@@ -290,3 +290,32 @@ def test_multigrid_pcg_matches_direct_path_on_unstructured_networks(name):
     assert _rel(out["dq"].cpu().numpy(), ref["dq"].cpu().numpy()) < TOL_G
     f, a = _lib.last_pcg_iterations()
     assert f <= 120 and a <= 120
+
+
+def test_disconnected_components_and_stalled_coarsening():
+    """
+    200 separate 3-node chains, each hanging from its own support: the multigrid hierarchy stops after one level at
+    200 rows without couplings (too many for the dense coarsest factor), and several right-hand-side columns are zero.
+    """
+    edges, fixed, xyz, loads = [], [], [], []
+    for k in range(200):
+        base = 4 * k
+        fixed += [1, 0, 0, 0]
+        for j in range(4):
+            xyz.append([float(k), 0.0, -float(j)])
+            loads.append([0.0, 0.0, 0.0 if j == 0 else -1.0 - 0.01 * k])
+        edges += [[base, base + 1], [base + 1, base + 2], [base + 2, base + 3]]
+    edges, fixed, xyz, loads = np.asarray(edges, dtype=np.int32), np.asarray(fixed, dtype=np.uint8), np.asarray(xyz), np.asarray(loads)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.info["mg_levels"] == 1 and plan.info["mg_n_coarsest"] == 200
+    rng = np.random.default_rng(4)
+    q = 1.0 + rng.random((3, len(edges)))
+    ref = Evaluator(plan, loads, xyz[plan.fixed], solver="direct").forward(q, outputs=("xyz", "residuals"))
+    for precond in ("multigrid", "jacobi"):
+        out = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", pcg_precond=precond).forward(q, outputs=("xyz", "residuals"))
+        assert np.all(out["status"].cpu().numpy() == 0)
+        assert _rel(out["xyz"].cpu().numpy(), ref["xyz"].cpu().numpy()) < TOL_X
+        assert _rel(out["residuals"].cpu().numpy(), ref["residuals"].cpu().numpy()) < 1e-8
+    # hanging chain under tension: z_j = z_{j-1} - (load below) / q
+    z = ref["xyz"].cpu().numpy()[0, 1, 2]
+    assert abs(z - (0.0 - 3.0 / q[0, 0])) < 1e-12
