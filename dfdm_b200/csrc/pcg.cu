@@ -745,53 +745,42 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, 
     }
 }
 
-// coarsest level: dense LDL^T per design in double precision, interleaved storage Lf[(i(i+1)/2 + j)][B]
-__global__ void k_mg_coarsest_factor(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col, int W, int B,
-                                     const mgf* __restrict__ vals, double* __restrict__ Lf) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// coarsest level: explicit inverse, one CTA per design - the operator is copied densely into shared memory
+// (double precision) and inverted in place by Gauss-Jordan elimination without pivoting (the operator is definite
+// whenever K is).  The cycle then applies the inverse as a dense product, parallel over rows, instead of a serial
+// substitution; the result is stored transposed-interleaved, inv[(j n + i)][B].
+__global__ void __launch_bounds__(256) k_mg_coarsest_invert(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col,
+                                                           int W, int B, const mgf* __restrict__ vals, mgf* __restrict__ inv) {
+    extern __shared__ double sA[];          // n x n, then a row and a column of scratch
+    double* rowk = sA + (size_t)n * n;
+    double* colk = rowk + n;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const size_t sB = (size_t)B;
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j <= i; ++j) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = 0.0;
-    for (int i = 0; i < n; ++i) {
+    for (int idx = tid; idx < n * n; idx += nt) sA[idx] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
         int k0 = rowptr[i], len = rowptr[i + 1] - k0;
-        for (int u = 0; u < len; ++u) {
-            int j = ell_col[(size_t)i * W + u];
-            if (j <= i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] = (double)vals[(size_t)(k0 + u) * sB + b];
+        for (int u = 0; u < len; ++u) sA[(size_t)i * n + ell_col[(size_t)i * W + u]] = (double)vals[(size_t)(k0 + u) * sB + b];
+    }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        const double pinv = 1.0 / sA[(size_t)k * n + k];
+        for (int j = tid; j < n; j += nt) {
+            rowk[j] = (j == k ? 1.0 : sA[(size_t)k * n + j]) * pinv;
+            colk[j] = sA[(size_t)j * n + k];
         }
-    }
-    // right-looking LDL^T in place: strictly lower part ends up holding L, the diagonal D
-    for (int j = 0; j < n; ++j) {
-        const double inv = 1.0 / Lf[(size_t)(j * (j + 1) / 2 + j) * sB + b];
-        for (int i = j + 1; i < n; ++i) {
-            const double lij = Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * inv;
-            for (int k = j + 1; k <= i; ++k)
-                Lf[(size_t)(i * (i + 1) / 2 + k) * sB + b] -= lij * Lf[(size_t)(k * (k + 1) / 2 + j) * sB + b];   // column j still unscaled
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += nt) {
+            int i = idx / n, j = idx - i * n;
+            if (i == k) sA[idx] = rowk[j];
+            else sA[idx] = (j == k ? 0.0 : sA[idx]) - colk[i] * rowk[j];
         }
-        for (int i = j + 1; i < n; ++i) Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] *= inv;
+        __syncthreads();
     }
-}
-
-// explicit inverse of the coarsest operator from its LDL^T: one thread per (column, design) solves for a unit vector.
-// The V-cycle then applies it as a dense product, which is parallel over rows instead of a serial substitution.
-__global__ void k_mg_coarsest_inverse(int n, int B, const double* __restrict__ Lf, double* __restrict__ work, mgf* __restrict__ inv) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * B) return;
-    int col = idx / B, b = idx - col * B;
-    const size_t sB = (size_t)B;
-    double* x = work + (size_t)col * n * sB + b;          // column `col`, entries at stride B
-    for (int i = 0; i < n; ++i) {
-        double yi = i == col ? 1.0 : 0.0;
-        for (int j = 0; j < i; ++j) yi -= Lf[(size_t)(i * (i + 1) / 2 + j) * sB + b] * x[(size_t)j * sB];
-        x[(size_t)i * sB] = yi;
+    for (int idx = tid; idx < n * n; idx += nt) {
+        int i = idx / n, j = idx - i * n;
+        inv[((size_t)j * n + i) * sB + b] = (mgf)sA[idx];
     }
-    for (int i = 0; i < n; ++i) x[(size_t)i * sB] /= Lf[(size_t)(i * (i + 1) / 2 + i) * sB + b];
-    for (int i = n - 1; i >= 0; --i) {
-        double xi = x[(size_t)i * sB];
-        for (int j = i + 1; j < n; ++j) xi -= Lf[(size_t)(j * (j + 1) / 2 + i) * sB + b] * x[(size_t)j * sB];
-        x[(size_t)i * sB] = xi;
-    }
-    for (int i = 0; i < n; ++i) inv[((size_t)col * n + i) * sB + b] = (mgf)x[(size_t)i * sB];
 }
 
 // coarsest solve: e = K_c^-1 b as a dense product; one thread per (row, coordinate, design)
@@ -802,9 +791,15 @@ __global__ void k_mg_coarsest_solve(int n, int B, const mgf* __restrict__ inv, c
     if (idx >= n * 3 * B) return;
     int b = idx % B, rc = idx / B, c = rc % 3, i = rc / 3;
     const size_t sB = (size_t)B;
-    float acc = 0.0f;
-    for (int j = 0; j < n; ++j) acc += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];   // symmetric: column j, row i
-    e[((size_t)i * 3 + c) * sB + b] = acc;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 1 < n; j += 2) {                                   // symmetric: column j, row i; two independent chains
+        acc0 += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];
+        acc1 += inv[((size_t)(j + 1) * n + i) * sB + b] * bvec[((size_t)(j + 1) * 3 + c) * sB + b];
+    }
+    if (j < n) acc0 += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];
+    e[((size_t)i * 3 + c) * sB + b] = acc0 + acc1;
 }
 
 // coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
@@ -1111,7 +1106,7 @@ static int lane_config(int B, LaneCfg& cfg, int max_rows) {
     return DFDM_OK;
 }
 
-constexpr int kCoarsestDense = 48;     // dense LDL^T on the coarsest level up to this many rows
+constexpr int kCoarsestDense = 128;    // explicit dense inverse of the coarsest operator up to this many rows (n^2 doubles of shared memory)
 
 struct MgBuffers {
     int n_levels = 0;                                  // coarse levels in use
@@ -1122,8 +1117,6 @@ struct MgBuffers {
     mgf* t[kMaxMgLevels + 1] = {nullptr};
     mgf* z[kMaxMgLevels + 1] = {nullptr};
     mgf* r2[kMaxMgLevels + 1] = {nullptr};             // W-cycle: residual after the first visit
-    double* Lf = nullptr;
-    double* inv_work = nullptr;
     mgf* inv = nullptr;
     mgf* tmp = nullptr;
 };
@@ -1158,8 +1151,6 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
         }
         int64_t nc = mg_n[mg_levels - 1];
         if (nc <= kCoarsestDense) {
-            w.mg.Lf = bump.take<double>(nc * (nc + 1) / 2 * B);
-            w.mg.inv_work = bump.take<double>(nc * nc * B);
             w.mg.inv = bump.take<mgf>(nc * nc * B);
         } else {
             w.mg.tmp = bump.take<mgf>(nc * 3 * B);
@@ -1308,11 +1299,15 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
         }
     }
     const MgLevelDev& C = M.lv[nl - 1];
-    if (w.mg.Lf) {
-        k_mg_coarsest_factor<<<(B + 63) / 64, 64, 0, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.Lf);
-        DFDM_LAUNCH_OK("k_mg_coarsest_factor");
-        k_mg_coarsest_inverse<<<(C.n * B + 127) / 128, 128, 0, st>>>(C.n, B, w.mg.Lf, w.mg.inv_work, w.mg.inv);
-        DFDM_LAUNCH_OK("k_mg_coarsest_inverse");
+    if (w.mg.inv) {
+        size_t smem = sizeof(double) * ((size_t)C.n * C.n + 2 * (size_t)C.n);
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            DFDM_CUDA_OK(cudaFuncSetAttribute(k_mg_coarsest_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_mg_coarsest_invert<<<B, 256, smem, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.inv);
+        DFDM_LAUNCH_OK("k_mg_coarsest_invert");
     }
     return DFDM_OK;
 }
@@ -1376,7 +1371,7 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
     const int nl = M.n_levels;
     if (l == nl) {
         const MgLevelDev& C = M.lv[nl - 1];
-        if (w.mg.Lf) {
+        if (w.mg.inv) {
             k_mg_coarsest_solve<<<(C.n * 3 * c.B + 255) / 256, 256, 0, c.st>>>(C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par);
             DFDM_LAUNCH_OK("k_mg_coarsest_solve");
         } else {

@@ -178,7 +178,7 @@ Graph match_pass(const Graph& g, std::vector<int32_t>& match) {
 // aggregation decisions only: agg[l] maps the rows of level l to the rows of level l+1
 static std::vector<std::vector<int32_t>> aggregate_levels(int n, const std::vector<int32_t>& rowptr,
                                                           const std::vector<int32_t>& colidx, std::vector<int>& sizes) {
-    constexpr int kCoarsest = 24;
+    constexpr int kCoarsest = 96;      // the coarsest operator is inverted densely in shared memory (pcg.cu, kCoarsestDense)
     std::vector<std::vector<int32_t>> aggs;
     Graph g = graph_from_csr(n, rowptr, colidx);
     sizes.assign(1, n);
