@@ -783,23 +783,38 @@ __global__ void __launch_bounds__(256) k_mg_coarsest_invert(int n, const int32_t
     }
 }
 
-// coarsest solve: e = K_c^-1 b as a dense product; one thread per (row, coordinate, design)
-__global__ void k_mg_coarsest_solve(int n, int B, const mgf* __restrict__ inv, const mgf* __restrict__ bvec, mgf* __restrict__ e,
-                                    const int32_t* __restrict__ n_active) {
+// coarsest solve: e = K_c^-1 b as a dense product.  A CTA owns 32 designs and 8 rows: the right-hand sides of its
+// designs are staged in shared memory once, every thread then streams one row of the (symmetric) inverse.
+__global__ void __launch_bounds__(256) k_mg_coarsest_solve(int n, int B, const mgf* __restrict__ inv, const mgf* __restrict__ bvec,
+                                                          mgf* __restrict__ e, const int32_t* __restrict__ n_active) {
     if (__ldcg(&n_active[1]) == 0) return;
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * 3 * B) return;
-    int b = idx % B, rc = idx / B, c = rc % 3, i = rc / 3;
+    extern __shared__ float sb[];                          // [n][3][32]
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const int i = blockIdx.y * 8 + rl;
     const size_t sB = (size_t)B;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    int j = 0;
-#pragma unroll 4
-    for (; j + 1 < n; j += 2) {                                   // symmetric: column j, row i; two independent chains
-        acc0 += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];
-        acc1 += inv[((size_t)(j + 1) * n + i) * sB + b] * bvec[((size_t)(j + 1) * 3 + c) * sB + b];
+    for (int idx = rl; idx < n * 3; idx += 8) sb[idx * 32 + lane] = b < B ? bvec[(size_t)idx * sB + b] : 0.0f;
+    __syncthreads();
+    if (b >= B || i >= n) return;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    const mgf* col = inv + (size_t)i * sB + b;             // inv[(j n + i)][b]: symmetric, so this is row i
+    constexpr int U = 10;                                  // loads of a batch are issued before their first use
+    const size_t stride = (size_t)n * sB;
+    for (int j0 = 0; j0 < n; j0 += U) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = j0 + u < n ? __ldg(col + (size_t)(j0 + u) * stride) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int j = min(j0 + u, n - 1);
+            a0 += a[u] * sb[(j * 3 + 0) * 32 + lane];
+            a1 += a[u] * sb[(j * 3 + 1) * 32 + lane];
+            a2 += a[u] * sb[(j * 3 + 2) * 32 + lane];
+        }
     }
-    if (j < n) acc0 += inv[((size_t)j * n + i) * sB + b] * bvec[((size_t)j * 3 + c) * sB + b];
-    e[((size_t)i * 3 + c) * sB + b] = acc0 + acc1;
+    e[((size_t)i * 3 + 0) * sB + b] = a0;
+    e[((size_t)i * 3 + 1) * sB + b] = a1;
+    e[((size_t)i * 3 + 2) * sB + b] = a2;
 }
 
 // coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
@@ -1372,7 +1387,9 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
     if (l == nl) {
         const MgLevelDev& C = M.lv[nl - 1];
         if (w.mg.inv) {
-            k_mg_coarsest_solve<<<(C.n * 3 * c.B + 255) / 256, 256, 0, c.st>>>(C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par);
+            dim3 grid((unsigned)((c.B + 31) / 32), (unsigned)((C.n + 7) / 8));
+            size_t smem = sizeof(float) * (size_t)C.n * 3 * 32;
+            k_mg_coarsest_solve<<<grid, 256, smem, c.st>>>(C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par);
             DFDM_LAUNCH_OK("k_mg_coarsest_solve");
         } else {
             MgMat A = mg_mat(*c.P, M, w, nl);
