@@ -717,6 +717,242 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The small levels of the hierarchy in ONE launch.  Below ~1 500 rows a level moves almost nothing and each of
+// its kernels costs a launch plus a chain of dependent loads (8-15 us); the plain V-cycle through those levels
+// (down ... coarsest dense solve ... up) therefore runs as a single kernel of thread-block clusters: a cluster of
+// 8 CTAs owns 16 design pairs, its 4 096 threads cover every row of a level in one or two passes, and the stages
+// are separated by cluster barriers (release / acquire at cluster scope, ~0.4 us) instead of kernel boundaries.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBottomMax = 6;            // levels inside the bottom kernel (without the coarsest)
+constexpr int kBottomCluster = 8;        // CTAs per cluster
+constexpr int kBottomThreads = 512;
+constexpr int kBottomLanes = 16;         // design pairs per cluster
+
+struct BottomArgs {
+    int count;                           // levels handled here; level k has operator A[k] and aggregates L[k] onto level k+1
+    MgMat A[kBottomMax];
+    MgLevelDev L[kBottomMax];
+    mgf* t[kBottomMax];
+    mgf* b[kBottomMax + 1];              // b[0] unused (the caller's right-hand side), b[k] = right-hand side of level k
+    mgf* z[kBottomMax + 1];              // z[k] = solution of level k (z[0] unused: the caller's output)
+    int n_coarsest;
+    const mgf* inv;
+    mgf* park0;                          // scratch of the first level's size (its own z belongs to the caller)
+};
+
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// vectors written earlier in the same launch by other CTAs of the cluster are read through L2 (ld.global.cg)
+__device__ __forceinline__ Vf<2> ldcg2(const float* p) {
+    float2 t = __ldcg(reinterpret_cast<const float2*>(p));
+    Vf<2> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+
+__global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, int B, const mgf* rhs, mgf* out, int acc,
+                                                              const int32_t* __restrict__ n_active, MgParams mp) {
+    if (__ldcg(&n_active[1]) == 0) return;                 // uniform over the grid: no CTA is left waiting at a barrier
+    constexpr int V = 2;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int cluster = blockIdx.x / kBottomCluster;
+    const int g = (int)rank * kBottomThreads + threadIdx.x;                 // thread index inside the cluster
+    const int lane = g % kBottomLanes, slot = g / kBottomLanes;
+    const int nslots = kBottomCluster * kBottomThreads / kBottomLanes;
+    const int b = (cluster * kBottomLanes + lane) * V;
+    const bool live = b < B;
+    const size_t sB = (size_t)B;
+
+    // ---- down: t = (K D^-1) rhs, coarse right-hand side = restricted smoothed residual -------------------
+    // two sub-stages per level, so that no thread walks an aggregate's members through a chain of dependent loads:
+    // (a) one thread per fine row: t and the smoothed residual (parked in z[k], which is free until the way up);
+    // (b) one thread per coarse row: sum of its members' residuals (consecutive rows in the hierarchical order).
+    for (int k = 0; k < a.count; ++k) {
+        const MgMat& A = a.A[k];
+        const MgLevelDev& L = a.L[k];
+        const mgf* bv = k == 0 ? rhs : a.b[k];
+        mgf* park = k == 0 ? a.park0 : a.z[k];
+        if (live) {
+            for (int f = slot; f < A.n; f += nslots) {
+                int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+                Vf<V> acc3[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc3[c].v[0] = acc3[c].v[1] = 0.0f;
+                constexpr int U = 5;
+                for (int u0 = 0; u0 < len; u0 += U) {
+                    int col[U];
+                    Vf<V> w[U], x0[U], x1[U], x2[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) col[u] = A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (u0 + u < len) w[u] = ldv<V>(A.vals_s + (size_t)(k0 + u0 + u) * sB + b);
+                        else w[u].v[0] = w[u].v[1] = 0.0f;
+                        const mgf* xj = bv + (size_t)col[u] * 3 * sB + b;
+                        x0[u] = ldcg2(xj);
+                        x1[u] = ldcg2(xj + sB);
+                        x2[u] = ldcg2(xj + 2 * sB);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            acc3[0].v[v] += w[u].v[v] * x0[u].v[v];
+                            acc3[1].v[v] += w[u].v[v] * x1[u].v[v];
+                            acc3[2].v[v] += w[u].v[v] * x2[u].v[v];
+                        }
+                }
+                size_t o = (size_t)f * 3 * sB + b;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    stv<V>(a.t[k] + o + c * sB, acc3[c]);
+                    Vf<V> bc = ldcg2(bv + o + c * sB), res;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) res.v[v] = bc.v[v] - mp.omega * acc3[c].v[v];
+                    stv<V>(park + o + c * sB, res);
+                }
+            }
+        }
+        cluster_barrier();
+        if (live) {
+            for (int I = slot; I < L.n; I += nslots) {
+                const int m0 = L.mem_ptr[I], m1 = L.mem_ptr[I + 1];
+                Vf<V> rc[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rc[c].v[0] = rc[c].v[1] = 0.0f;
+                for (int m = m0; m < m1; ++m) {               // independent loads: members are rows m0 .. m1-1
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        Vf<V> r1 = ldcg2(park + ((size_t)m * 3 + c) * sB + b);
+                        rc[c].v[0] += r1.v[0];
+                        rc[c].v[1] += r1.v[1];
+                    }
+                }
+                size_t oc = (size_t)I * 3 * sB + b;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) stv<V>(a.b[k + 1] + oc + c * sB, rc[c]);
+            }
+        }
+        cluster_barrier();
+    }
+    // ---- coarsest: dense product with the explicit inverse; the right-hand sides are staged in shared memory ----
+    {
+        const int n = a.n_coarsest;
+        const mgf* bv = a.b[a.count];
+        mgf* e = a.z[a.count];
+        extern __shared__ float sbot[];                    // [n][3][kBottomLanes][2]
+        const int b_first = cluster * kBottomLanes * V;
+        for (int idx = threadIdx.x; idx < n * 3 * kBottomLanes; idx += kBottomThreads) {
+            int ln = idx % kBottomLanes, jc = idx / kBottomLanes;
+            int bb = b_first + ln * V;
+            Vf<V> val;
+            val.v[0] = val.v[1] = 0.0f;
+            if (bb < B) val = ldcg2(bv + (size_t)jc * sB + bb);
+            sbot[idx * 2] = val.v[0];
+            sbot[idx * 2 + 1] = val.v[1];
+        }
+        __syncthreads();
+        if (live) {
+            for (int i = slot; i < n; i += nslots) {
+                float s0[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f}, s2[2] = {0.0f, 0.0f};
+                constexpr int U = 14;
+                const size_t stride = (size_t)n * sB;
+                for (int j0 = 0; j0 < n; j0 += U) {
+                    Vf<V> w[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        w[u] = ldv<V>(a.inv + (size_t)min(j0 + u, n - 1) * stride + (size_t)i * sB + b);
+                        if (j0 + u >= n) w[u].v[0] = w[u].v[1] = 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float* sj = sbot + ((size_t)(min(j0 + u, n - 1) * 3) * kBottomLanes + lane) * 2;
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            s0[v] += w[u].v[v] * sj[v];
+                            s1[v] += w[u].v[v] * sj[kBottomLanes * 2 + v];
+                            s2[v] += w[u].v[v] * sj[2 * kBottomLanes * 2 + v];
+                        }
+                    }
+                }
+                size_t o = (size_t)i * 3 * sB + b;
+                Vf<V> o0, o1, o2;
+                o0.v[0] = s0[0]; o0.v[1] = s0[1]; o1.v[0] = s1[0]; o1.v[1] = s1[1]; o2.v[0] = s2[0]; o2.v[1] = s2[1];
+                stv<V>(e + o, o0);
+                stv<V>(e + o + sB, o1);
+                stv<V>(e + o + 2 * sB, o2);
+            }
+        }
+        cluster_barrier();
+    }
+    // ---- up: z = x' + w D^-1 (b - K x'), x' = w D^-1 b + s P e ------------------------------------------------
+    for (int k = a.count - 1; k >= 0; --k) {
+        const MgMat& A = a.A[k];
+        const MgLevelDev& L = a.L[k];
+        const mgf* bv = k == 0 ? rhs : a.b[k];
+        const mgf* ec = a.z[k + 1];
+        mgf* zo = k == 0 ? out : a.z[k];
+        if (live) {
+            for (int f = slot; f < A.n; f += nslots) {
+                int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+                Vf<V> sacc[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sacc[c].v[0] = sacc[c].v[1] = 0.0f;
+                constexpr int U = 5;
+                for (int u0 = 0; u0 < len; u0 += U) {
+                    int cg[U];
+                    Vf<V> w[U], x0[U], x1[U], x2[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) cg[u] = L.agg[A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)]];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (u0 + u < len) w[u] = ldv<V>(A.vals + (size_t)(k0 + u0 + u) * sB + b);
+                        else w[u].v[0] = w[u].v[1] = 0.0f;
+                        const mgf* ej = ec + (size_t)cg[u] * 3 * sB + b;
+                        x0[u] = ldcg2(ej);
+                        x1[u] = ldcg2(ej + sB);
+                        x2[u] = ldcg2(ej + 2 * sB);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            sacc[0].v[v] += w[u].v[v] * x0[u].v[v];
+                            sacc[1].v[v] += w[u].v[v] * x1[u].v[v];
+                            sacc[2].v[v] += w[u].v[v] * x2[u].v[v];
+                        }
+                }
+                Vf<V> wd = ldv<V>(A.dinv + (size_t)f * sB + b);
+                const mgf* ei = ec + (size_t)L.agg[f] * 3 * sB + b;
+                size_t o = (size_t)f * 3 * sB + b;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Vf<V> bc = ldcg2(bv + o + c * sB), tc = ldcg2(a.t[k] + o + c * sB), e1 = ldcg2(ei + c * sB), zc;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        float w1 = mp.omega * wd.v[v];
+                        float xn = w1 * bc.v[v] + mp.over * e1.v[v];
+                        zc.v[v] = xn + w1 * (bc.v[v] - mp.omega * tc.v[v] - mp.over * sacc[c].v[v]);
+                    }
+                    if (k == 0 && acc) {
+                        Vf<V> prev = ldcg2(zo + o + c * sB);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) zc.v[v] += prev.v[v];
+                    }
+                    stv<V>(zo + o + c * sB, zc);
+                }
+            }
+        }
+        if (k > 0) cluster_barrier();
+    }
+}
+
 // W-cycle helper on a coarse level: r2 = rhs - A x
 template <int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, int B, const mgf* __restrict__ rhs,
@@ -1349,6 +1585,7 @@ struct MgCtx {
     MgParams mp;
     LaneCfg vbase;
     int w_levels;          // coarse levels 1 .. w_levels are visited twice per visit of their parent (W-cycle)
+    int bottom;            // first level handled by the single-launch bottom kernel (0: none)
 };
 
 // out = M_l rhs on coarse level l (1 <= l <= n_levels): exact on the coarsest level, one (V) or two (W) cycles above it
@@ -1379,11 +1616,48 @@ static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out, const
     return DFDM_OK;
 }
 
+// levels c.bottom .. coarsest in one cluster launch: out (+)= M_l rhs
+static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
+    const MgDev& M = *c.M;
+    PcgBuffers& w = *c.w;
+    const int nl = M.n_levels, l0 = c.bottom;
+    BottomArgs a{};
+    a.count = nl - l0;
+    for (int k = 0; k < a.count; ++k) {
+        a.A[k] = mg_mat(*c.P, M, w, l0 + k);
+        a.L[k] = M.lv[l0 + k];
+        a.t[k] = w.mg.t[l0 + k];
+        a.b[k + 1] = w.mg.b[l0 + k + 1];
+        a.z[k + 1] = w.mg.z[l0 + k + 1];
+    }
+    a.n_coarsest = M.lv[nl - 1].n;
+    a.inv = w.mg.inv;
+    a.park0 = w.mg.r2[l0];                                   // free here: the bottom levels are never W levels
+    const int pairs = c.B / 2;
+    const int nclusters = (pairs + kBottomLanes - 1) / kBottomLanes;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nclusters * kBottomCluster));
+    cfg.blockDim = dim3(kBottomThreads);
+    cfg.dynamicSmemBytes = sizeof(float) * (size_t)a.n_coarsest * 3 * kBottomLanes * 2;
+    cfg.stream = c.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBottomCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mg_bottom, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp));
+    DFDM_LAUNCH_OK("k_mg_bottom");
+    return DFDM_OK;
+}
+
 template <int V>
 static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
     const MgDev& M = *c.M;
     PcgBuffers& w = *c.w;
     const int nl = M.n_levels;
+    if (V == 2 && c.bottom > 0 && l == c.bottom) return mg_bottom(c, rhs, out, 0);
     if (l == nl) {
         const MgLevelDev& C = M.lv[nl - 1];
         if (w.mg.inv) {
@@ -1416,7 +1690,14 @@ template <int V>
 static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, int first, cudaStream_t st, size_t& used,
                        MgParams mp, int w_levels) {
     static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1), up_tiles = tile_factor("DFDM_TILE_UP", 4);
-    MgCtx c{&P, &M, &w, B, st, mp, vec_base(B, V), w_levels};
+    // the bottom kernel takes over at the first level with few rows, below the W levels, when the coarsest inverse is dense
+    static const int bottom_rows = tile_factor("DFDM_MG_BOTTOM", 24) * 64;
+    int bottom = 0;
+    if (V == 2 && w.mg.inv && M.lv[M.n_levels - 1].n <= 120) {       // right-hand sides of the coarsest level fit 48 KB
+        for (int l = std::max(1, w_levels + 1); l < M.n_levels; ++l)
+            if (M.lv[l - 1].n <= bottom_rows && M.n_levels - l <= kBottomMax) { bottom = l; break; }
+    }
+    MgCtx c{&P, &M, &w, B, st, mp, vec_base(B, V), w_levels, bottom};
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     MgMat A = mg_mat(P, M, w, 0);
     LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
