@@ -9,6 +9,19 @@ for p in (ROOT, os.path.dirname(__file__)):
         sys.path.insert(0, p)
 
 
+def _ensure_library():
+    """The CUDA library is built in-tree (nvcc cross-compiles without a GPU); a fresh checkout has no .so yet."""
+    try:
+        from dfdm_b200 import build as _build
+        if _build.stale():
+            _build.build()
+    except Exception as exc:          # the tests that need the library will fail loudly on import
+        print("dfdm_b200: could not build libdfdm_b200.so: %s" % exc)
+
+
+_ensure_library()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
