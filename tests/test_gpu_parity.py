@@ -319,3 +319,27 @@ def test_disconnected_components_and_stalled_coarsening():
     # hanging chain under tension: z_j = z_{j-1} - (load below) / q
     z = ref["xyz"].cpu().numpy()[0, 1, 2]
     assert abs(z - (0.0 - 3.0 / q[0, 0])) < 1e-12
+
+
+@pytest.mark.parametrize("batch", [10, 100])
+def test_pcg_with_force_densities_spanning_orders_of_magnitude(batch):
+    """q log-uniform in [0.05, 20]: strongly varying coefficients, batch sizes that do not fill warps or chunks."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(48)
+    plan = Plan(len(fixed), edges, fixed)
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg")
+    rng = np.random.default_rng(21)
+    q = 10.0 ** rng.uniform(np.log10(0.05), np.log10(20.0), size=(batch, len(q0)))
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("MeanSquaredError", 2.0)], 0.0)
+    out = ev.loss_and_grad(prog, q, outputs=("xyz",))
+    assert np.all(out["status"].cpu().numpy() == 0)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    for b in (0, batch // 2, batch - 1):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 2.0 / len(edges), 0.0)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+    f, a = _lib.last_pcg_iterations()
+    assert f < 400 and a < 400           # the multigrid preconditioner holds without the Jacobi fallback
