@@ -18,7 +18,7 @@ from scipy.optimize import minimize
 from dfdm_b200.equilibrium.model import EquilibriumModel
 
 __all__ = ["Optimizer", "ConstrainedOptimizer", "BFGS", "SLSQP", "TrustRegionConstrained", "OptimizationRecorder",
-           "BatchedGradientDescent"]
+           "BatchedGradientDescent", "BatchedLBFGS"]
 
 
 class Optimizer:
@@ -166,3 +166,102 @@ class BatchedGradientDescent:
                 break
         self.history = history
         return q, value
+
+
+class BatchedLBFGS:
+    """
+    Lock-step projected L-BFGS over a batch of designs ``q[B, E]`` with box bounds.
+
+    Every design keeps its own curvature pairs, step length and convergence flag; what is shared is the
+    evaluation: one batched CUDA call per trial point returns the loss and gradient of all designs.  The
+    search direction is the two-loop recursion on the free variables (those not pinned at a bound with
+    the gradient pointing outward), the step is found by backtracking on the Armijo condition along the
+    projected path, and designs that have converged stop moving.  ``fun(q) -> (loss[B], grad[B, E])`` is
+    any callable with that contract; ``minimize(model, loss, q0, ...)`` builds it from a ``Loss``.
+    """
+    def __init__(self, memory=8, maxiter=100, gtol=1e-6, ftol=1e-10, armijo=1e-4, max_backtracks=12):
+        self.memory, self.maxiter, self.gtol, self.ftol = memory, maxiter, gtol, ftol
+        self.armijo, self.max_backtracks = armijo, max_backtracks
+
+    def minimize(self, model, loss, q0, bounds=(None, None), callback=None):
+        return self.minimize_fun(lambda q: loss.value_and_grad(q, model), q0, bounds, callback)
+
+    def minimize_fun(self, fun, q0, bounds=(None, None), callback=None):
+        lb = -np.inf if bounds[0] is None else bounds[0]
+        ub = np.inf if bounds[1] is None else bounds[1]
+        q = np.clip(np.array(q0, dtype=np.float64, copy=True), lb, ub)
+        B, E = q.shape
+        f, g = fun(q)
+        f, g = np.array(f, dtype=np.float64), np.array(g, dtype=np.float64)
+        S, Y = [], []                                    # curvature pairs, each [B, E]; rho per design
+        active = np.ones(B, dtype=bool)
+        self.evaluations = 1
+        history = [f.copy()]
+
+        def projected_gradient(q, g):
+            pg = g.copy()
+            pg[(q <= lb) & (g > 0)] = 0.0
+            pg[(q >= ub) & (g < 0)] = 0.0
+            return pg
+
+        for it in range(self.maxiter):
+            pg = projected_gradient(q, g)
+            active &= np.max(np.abs(pg), axis=1) > self.gtol
+            if not active.any():
+                break
+            free = pg != 0.0
+            # two-loop recursion, vectorised over designs
+            d = pg.copy()
+            alphas = []
+            for s_k, y_k in zip(reversed(S), reversed(Y)):
+                sy = np.sum(s_k * y_k, axis=1)
+                ok = sy > 1e-300
+                a = np.where(ok, np.sum(s_k * d, axis=1) / np.where(ok, sy, 1.0), 0.0)
+                d -= a[:, None] * y_k
+                alphas.append((a, ok, sy))
+            if S:
+                sy = np.sum(S[-1] * Y[-1], axis=1)
+                yy = np.sum(Y[-1] * Y[-1], axis=1)
+                gamma = np.where((sy > 1e-300) & (yy > 0), sy / np.where(yy > 0, yy, 1.0), 1.0)
+                d *= gamma[:, None]
+            for (a, ok, sy), s_k, y_k in zip(reversed(alphas), S, Y):
+                b = np.where(ok, np.sum(y_k * d, axis=1) / np.where(ok, sy, 1.0), 0.0)
+                d += (a - b)[:, None] * s_k
+            d = -np.where(free, d, 0.0)
+            slope = np.sum(pg * d, axis=1)
+            bad = slope >= 0                              # not a descent direction: fall back to steepest descent
+            d[bad] = -pg[bad]
+            slope = np.sum(pg * d, axis=1)
+            # backtracking along the projected path; per-design step lengths, one batched evaluation per trial
+            t = np.ones(B) if S else np.minimum(1.0, 1.0 / np.maximum(np.max(np.abs(pg), axis=1), 1e-300))
+            todo = active.copy()
+            q_new, f_new, g_new = q.copy(), f.copy(), g.copy()
+            for _ in range(self.max_backtracks):
+                trial = np.where(todo[:, None], np.clip(q + t[:, None] * d, lb, ub), q_new)
+                ft, gt = fun(trial)
+                self.evaluations += 1
+                ft, gt = np.asarray(ft, dtype=np.float64), np.asarray(gt, dtype=np.float64)
+                decrease = np.sum(pg * (trial - q), axis=1)
+                accept = todo & np.isfinite(ft) & (ft <= f + self.armijo * decrease)
+                q_new[accept], f_new[accept], g_new[accept] = trial[accept], ft[accept], gt[accept]
+                todo &= ~accept
+                if not todo.any():
+                    break
+                t = np.where(todo, 0.5 * t, t)
+            active &= ~todo                               # no acceptable step: that design is done
+            s_k, y_k = q_new - q, g_new - g
+            moved = np.any(s_k != 0.0, axis=1)
+            small = np.abs(f - f_new) <= self.ftol * np.maximum(1.0, np.abs(f_new))
+            active &= ~(moved & small)
+            S.append(np.where(moved[:, None], s_k, 0.0))
+            Y.append(np.where(moved[:, None], y_k, 0.0))
+            if len(S) > self.memory:
+                S.pop(0)
+                Y.pop(0)
+            q, f, g = q_new, f_new, g_new
+            history.append(f.copy())
+            if callback is not None:
+                callback(q, f)
+        self.history = history
+        self.iterations = len(history) - 1
+        return q, f

@@ -14,7 +14,7 @@ from dfdm_b200 import workloads
 from dfdm_b200.equilibrium import EquilibriumModel
 from dfdm_b200.goals import NodeLineGoal
 from dfdm_b200.losses import Loss, SquaredError
-from dfdm_b200.optimization import BatchedGradientDescent
+from dfdm_b200.optimization import BatchedLBFGS
 
 
 def main(batch=4096, maxiter=30, verbose=True):
@@ -31,10 +31,12 @@ def main(batch=4096, maxiter=30, verbose=True):
     t0 = time.perf_counter()
     value, grad = loss.value_and_grad(q, model)
     dt = time.perf_counter() - t0
-    q_opt, value_opt = BatchedGradientDescent(step=1e-1, maxiter=maxiter).minimize(model, loss, q, bounds=(None, -1e-3))
+    optimizer = BatchedLBFGS(maxiter=maxiter)
+    q_opt, value_opt = optimizer.minimize(model, loss, q, bounds=(None, -1e-3))
     if verbose:
         print(f"{batch} designs: loss + gradient in {1e3 * dt:.2f} ms through the Python API ({batch / dt:.0f} evals/s incl. copies)")
-        print(f"mean loss {value.mean():.5f} -> {value_opt.mean():.5f} after {maxiter} lock-step iterations")
+        print(f"mean loss {value.mean():.5f} -> {value_opt.mean():.5f} after {optimizer.iterations} lock-step L-BFGS iterations "
+              f"({optimizer.evaluations} batched evaluations)")
     return value, value_opt
 
 

@@ -232,3 +232,31 @@ def test_reference_import_paths_resolve_after_compat_install():
             "from dfdm.optimization import SLSQP, BFGS, TrustRegionConstrained, OptimizationRecorder; print('ok')") % os.path.join(os.path.dirname(__file__), "..")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_batched_lbfgs_matches_scipy_on_a_batch_of_bounded_quadratics():
+    """The lock-step optimiser against SciPy's L-BFGS-B, design by design, on problems with a known gradient."""
+    from scipy.optimize import minimize
+    from dfdm_b200.optimization import BatchedLBFGS
+    rng = np.random.default_rng(0)
+    B, E = 6, 12
+    A = rng.standard_normal((B, E, E))
+    H = np.einsum("bij,bkj->bik", A, A) + 0.5 * np.eye(E)
+    c = rng.standard_normal((B, E))
+
+    def fun(q):
+        Hq = np.einsum("bij,bj->bi", H, q)
+        return 0.5 * np.sum(q * Hq, axis=1) + np.sum(c * q, axis=1) + 0.1 * np.sum(q ** 4, axis=1), Hq + c + 0.4 * q ** 3
+
+    q0 = rng.standard_normal((B, E))
+    q, f = BatchedLBFGS(memory=10, maxiter=200, gtol=1e-9).minimize_fun(fun, q0, bounds=(-0.3, 0.5))
+    for b in range(B):
+        def one(x, b=b):
+            full = np.zeros((B, E))
+            full[b] = x
+            v, g = fun(full)
+            return v[b], g[b]
+        ref = minimize(one, q0[b].clip(-0.3, 0.5), jac=True, method="L-BFGS-B", bounds=[(-0.3, 0.5)] * E, options={"ftol": 1e-15, "gtol": 1e-10})
+        assert abs(f[b] - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
+        assert np.max(np.abs(q[b] - ref.x)) < 1e-4
+    assert np.all(q >= -0.3) and np.all(q <= 0.5)

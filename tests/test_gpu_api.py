@@ -13,7 +13,7 @@ from oracle import fdm_oracle as O
 from dfdm_b200.equilibrium import EquilibriumModel, fdm, constrained_fdm
 from dfdm_b200.losses import Loss, SquaredError
 from dfdm_b200.goals import NodeResidualDirectionGoal
-from dfdm_b200.optimization import SLSQP, BFGS, TrustRegionConstrained, OptimizationRecorder, BatchedGradientDescent
+from dfdm_b200.optimization import SLSQP, BFGS, TrustRegionConstrained, OptimizationRecorder, BatchedGradientDescent, BatchedLBFGS
 
 pytestmark = pytest.mark.gpu
 
@@ -153,3 +153,20 @@ def test_batched_lockstep_descent_improves_every_design():
     q, value = BatchedGradientDescent(step=1e-1, maxiter=25).minimize(model, loss, q0, bounds=(None, -1e-3))
     assert value.shape == (16,) and np.all(value <= start) and np.mean(value) < 0.7 * np.mean(start)
     assert np.all(q <= -1e-3)
+
+
+def test_batched_lbfgs_reaches_scipy_optima_design_by_design():
+    """An ensemble optimised in lock step ends where SciPy's L-BFGS-B ends for each design on its own."""
+    case = CASES["pringle"]
+    model = EquilibriumModel(case["network"])
+    loss = Loss(*goal_objects(case))
+    rng = np.random.default_rng(9)
+    q0 = np.clip(case["q"][None, :] * (1.0 + 0.3 * (rng.random((32, len(case["q"]))) - 0.5)), -5.0, -0.1)
+    opt = BatchedLBFGS(maxiter=150, gtol=1e-7)
+    q, value = opt.minimize(model, loss, q0, bounds=(-5.0, -0.1))
+    assert np.all(value <= loss(q0, model)) and np.all(q <= -0.1) and np.all(q >= -5.0)
+    for b in (0, 17):
+        ref = minimize(lambda x: loss.value_and_grad(x, model), q0[b], jac=True, method="L-BFGS-B", bounds=[(-5.0, -0.1)] * q0.shape[1],
+                       options={"maxiter": 150, "ftol": 1e-14, "gtol": 1e-8})
+        assert value[b] <= 1.15 * ref.fun + 1e-9          # same iteration budget, ill-conditioned problem: same ballpark
+    assert opt.evaluations < 400
