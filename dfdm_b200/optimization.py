@@ -18,7 +18,7 @@ from scipy.optimize import minimize
 from dfdm_b200.equilibrium.model import EquilibriumModel
 
 __all__ = ["Optimizer", "ConstrainedOptimizer", "BFGS", "SLSQP", "TrustRegionConstrained", "OptimizationRecorder",
-           "BatchedGradientDescent", "BatchedLBFGS"]
+           "BatchedGradientDescent", "BatchedLBFGS", "StackedConstraints"]
 
 
 class Optimizer:
@@ -74,14 +74,64 @@ class Optimizer:
 
 class ConstrainedOptimizer(Optimizer):
     def constraints(self, constraints, model):
+        """
+        The reference hands SciPy one NonlinearConstraint per constraint object, each with its own
+        ``autograd.jacobian`` (optimization.py:115-130): every object re-solves the equilibrium for its value
+        and once more per Jacobian row.  Here all constraints are stacked into ONE vector constraint
+        (equivalent for SLSQP and trust-constr): its value reads the cached state of the current ``q`` and
+        its Jacobian is a single batched VJP with one design per constraint row.
+        """
         if not constraints:
             return ()
-        clist = []
-        for constraint in constraints:
-            fun = (lambda x, c=constraint: np.atleast_1d(c(x, model)))
-            jac = (lambda x, c=constraint: c.jacobian(x, model))
-            clist.append(NonlinearConstraint(fun=fun, jac=jac, lb=constraint.bound_low, ub=constraint.bound_up))
-        return clist
+        return [StackedConstraints(constraints, model).as_scipy()]
+
+
+class StackedConstraints:
+    """Several constraint objects as one vector-valued constraint with a batched Jacobian."""
+    STATE = ("xyz", "residuals", "vectors", "lengths", "forces")
+
+    def __init__(self, constraints, model):
+        self.constraints = list(constraints)
+        self.model = model
+
+    def values(self, q):
+        return np.concatenate([np.atleast_1d(np.asarray(c(q, self.model), dtype=np.float64)) for c in self.constraints])
+
+    def bounds(self, q):
+        lows, ups = [], []
+        for c in self.constraints:
+            m = np.atleast_1d(np.asarray(c(q, self.model))).shape[0]
+            lows.append(np.broadcast_to(np.asarray(c.bound_low, dtype=np.float64), (m,)))
+            ups.append(np.broadcast_to(np.asarray(c.bound_up, dtype=np.float64), (m,)))
+        return np.concatenate(lows), np.concatenate(ups)
+
+    def jacobian(self, q):
+        from dfdm_b200.constraints.constraint import _cached_state
+        from dfdm_b200.engine import Evaluator
+        q = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+        model = self.model
+        eqstate = _cached_state(q, model)
+        parts = [c.cotangents(eqstate, model) for c in self.constraints]
+        sizes = [next(iter(p.values())).shape[0] for p in parts]
+        total = sum(sizes)
+        n, E = model.plan.n, model.plan.n_edges
+        shapes = {"xyz": (total, n, 3), "residuals": (total, n, 3), "vectors": (total, E, 3), "lengths": (total, E), "forces": (total, E)}
+        stacked = {}
+        row = 0
+        for p, m in zip(parts, sizes):
+            for name, arr in p.items():
+                if name not in stacked:
+                    stacked[name] = np.zeros(shapes[name])
+                stacked[name][row:row + m] = arr
+            row += m
+        dq, status = model.evaluator.vjp(np.repeat(q[None, :], total, axis=0), **stacked)
+        Evaluator.raise_on_status(status)
+        return dq.cpu().numpy()
+
+    def as_scipy(self):
+        q0 = np.asarray(self.model.structure.network.edges_forcedensities(), dtype=np.float64)
+        lb, ub = self.bounds(q0)
+        return NonlinearConstraint(fun=self.values, jac=self.jacobian, lb=lb, ub=ub)
 
 
 class BFGS(Optimizer):

@@ -170,3 +170,20 @@ def test_batched_lbfgs_reaches_scipy_optima_design_by_design():
                        options={"maxiter": 150, "ftol": 1e-14, "gtol": 1e-8})
         assert value[b] <= 1.15 * ref.fun + 1e-9          # same iteration budget, ill-conditioned problem: same ballpark
     assert opt.evaluations < 400
+
+
+def test_stacked_constraints_equal_the_individual_ones():
+    from dfdm_b200.optimization import StackedConstraints
+    case = CASES["pillow"]
+    g = np.load(os.path.join(GOLDEN, "pillow.npz"))
+    model = EquilibriumModel(case["network"])
+    cons = constraint_objects(case)
+    stacked = StackedConstraints(cons, model)
+    values = stacked.values(g["q"])
+    jac = stacked.jacobian(g["q"])
+    want_v = np.concatenate([g["constraint_%d" % k] for k in range(len(cons))])
+    want_j = np.concatenate([g["constraint_jac_%d" % k] for k in range(len(cons))])
+    assert values.shape == want_v.shape and jac.shape == want_j.shape
+    assert _rel(values, want_v) < 1e-9 and _rel(jac, want_j) < 1e-7
+    lb, ub = stacked.bounds(g["q"])
+    assert lb.shape == want_v.shape and np.all(lb == 0.0) and np.all(ub == 1.0)
