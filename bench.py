@@ -235,6 +235,8 @@ def gpu_arm(args, rank, world, local_rank):
     q_dev = q_host.to(device)
     E = plan.n_edges
     solver = plan.auto_solver if args.solver == "auto" else args.solver
+    if args.steps <= 0:
+        args.steps = 3 if solver == "pcg" else 50
 
     def step():
         out = ev.loss_and_grad(prog, q_dev)
@@ -367,7 +369,9 @@ def reference_arm(args, rank, world):
         return None
     batch = args.batch or DEFAULT_BATCH.get(args.workload, 256)
     wl = make_workload(args.workload, batch)
-    v, cores, desc, ms = cpu_arm(wl, budget_s=args.cpu_budget, steps=max(1, args.steps))
+    if args.steps <= 0:
+        args.steps = 3
+    v, cores, desc, ms = cpu_arm(wl, budget_s=args.cpu_budget, steps=args.steps)
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -380,7 +384,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 3; 50 for the sub-millisecond steps of the direct path)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="grid256")

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <string>

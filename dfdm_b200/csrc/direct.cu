@@ -22,6 +22,7 @@ struct DirectArgs {
     GoalProgDev G;
     int has_prog, adjoint, B;
     int tx_shift;                    // threads along a band row in the trailing update = 1 << tx_shift
+    int k_shift;                     // 1 << k_shift >= bandwidth: band offsets per right-hand side in the solves
     const double* q;
     const double* loads;
     const double* xfix;
@@ -49,28 +50,31 @@ __device__ double cta_sum(double v, double* red, int nt) {
     return s;
 }
 
-// Solve (L D L^T) x = rhs for the 3 columns in shared memory.
-__device__ void band_solve(const double* __restrict__ D, double* __restrict__ rhs, int nf, int w, int LD, int nt) {
+// Solve (L D L^T) x = rhs for the 3 columns in shared memory.  A thread owns (column c, band offset k)
+// with k in the low kshift bits of its index, so the hot loops carry no integer division.
+__device__ void band_solve(const double* __restrict__ D, double* __restrict__ rhs, int nf, int w, int LD, int nt, int kshift) {
     const int tid = threadIdx.x;
+    const int span = 3 << kshift, kmask = (1 << kshift) - 1;
     for (int j = 0; j < nf - 1; ++j) {                       // forward: L y = b
         int m = min(w, nf - 1 - j);
-        for (int idx = tid; idx < 3 * m; idx += nt) {
-            int c = idx / m, k = idx - c * m + 1;
-            rhs[c * nf + j + k] -= D[k * LD + j + k] * rhs[c * nf + j];
+        for (int t = tid; t < span; t += nt) {
+            int c = t >> kshift, k = (t & kmask) + 1;
+            if (k <= m) rhs[c * nf + j + k] -= D[k * LD + j + k] * rhs[c * nf + j];
         }
         cta_sync(nt);
     }
-    for (int idx = tid; idx < 3 * nf; idx += nt) {           // D z = y
-        int c = idx / nf, i = idx - c * nf;
-        rhs[idx] /= D[i];
-        (void)c;
+    for (int i = tid; i < nf; i += nt) {                     // D z = y
+        double d = D[i];
+        rhs[i] /= d;
+        rhs[nf + i] /= d;
+        rhs[2 * nf + i] /= d;
     }
     cta_sync(nt);
     for (int j = nf - 1; j > 0; --j) {                       // backward: L^T x = z
         int m = min(w, j);
-        for (int idx = tid; idx < 3 * m; idx += nt) {
-            int c = idx / m, k = idx - c * m + 1;
-            rhs[c * nf + j - k] -= D[k * LD + j] * rhs[c * nf + j];
+        for (int t = tid; t < span; t += nt) {
+            int c = t >> kshift, k = (t & kmask) + 1;
+            if (k <= m) rhs[c * nf + j - k] -= D[k * LD + j] * rhs[c * nf + j];
         }
         cta_sync(nt);
     }
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
         }
 
         // ---- forward solve and equilibrium state ------------------------------------------------------
-        band_solve(D, rhs, nf, w, LD, nt);
+        band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
         for (int i = tid; i < n; i += nt) {
             int src = P.node_src[i];
             if (src >= 0) {
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
                 rhs[2 * nf + p] = xb[2];
             }
             cta_sync(nt);
-            band_solve(D, rhs, nf, w, LD, nt);       // K symmetric: same factor
+            band_solve(D, rhs, nf, w, LD, nt, a.k_shift);       // K symmetric: same factor
             for (int e = tid; e < E; e += nt) {
                 int su = P.node_src[P.edges[2 * e]], sv = P.node_src[P.edges[2 * e + 1]];
                 double d = 0.0;
@@ -356,14 +360,21 @@ int run_direct(Eval& ev) {
     int shift = 0;
     while ((1 << shift) < tx) ++shift;
     a.tx_shift = shift;
+    int kshift = 0;
+    while ((1 << kshift) < w) ++kshift;
+    a.k_shift = kshift;
     int64_t smem = direct_smem_bytes(P.nf, w);
-    static thread_local int64_t configured = -1;
-    if (smem > 48 * 1024 && smem != configured) {
-        DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     int dev = 0, sms = 0, per_sm = 0;
     DFDM_CUDA_OK(cudaGetDevice(&dev));
+    if (smem > 48 * 1024) {                               // opt-in is per device and per function: set it wherever we launch
+        static std::mutex mu;
+        static std::map<int, int64_t> configured;
+        std::lock_guard<std::mutex> lock(mu);
+        if (configured[dev] < smem) {
+            DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = smem;
+        }
+    }
     DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_eval, nt, (size_t)smem));
     if (per_sm < 1) per_sm = 1;

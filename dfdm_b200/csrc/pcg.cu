@@ -721,13 +721,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
 // The small levels of the hierarchy in ONE launch.  Below ~1 500 rows a level moves almost nothing and each of
 // its kernels costs a launch plus a chain of dependent loads (8-15 us); the plain V-cycle through those levels
 // (down ... coarsest dense solve ... up) therefore runs as a single kernel of thread-block clusters: a cluster of
-// 8 CTAs owns 16 design pairs, its 4 096 threads cover every row of a level in one or two passes, and the stages
+// 8 CTAs owns LANES design pairs, its 4 096 threads cover every row of a level in a few passes, and the stages
 // are separated by cluster barriers (release / acquire at cluster scope, ~0.4 us) instead of kernel boundaries.
+// What is left is latency: every row is a chain row pointer -> column index -> (aggregate ->) vector element.
+// The index part of that chain is the same for every design, so each CTA copies it for ITS rows into shared
+// memory once per launch; the loops then issue only the value and vector loads, all independent.
 // ------------------------------------------------------------------------------------------------
 constexpr int kBottomMax = 6;            // levels inside the bottom kernel (without the coarsest)
 constexpr int kBottomCluster = 8;        // CTAs per cluster
 constexpr int kBottomThreads = 512;
-constexpr int kBottomLanes = 16;         // design pairs per cluster
+#ifndef DFDM_BOTTOM_U
+#define DFDM_BOTTOM_U 5
+#endif
+constexpr int kBottomU = DFDM_BOTTOM_U;  // matrix entries in flight per thread
 
 struct BottomArgs {
     int count;                           // levels handled here; level k has operator A[k] and aggregates L[k] onto level k+1
@@ -739,7 +745,12 @@ struct BottomArgs {
     int n_coarsest;
     const mgf* inv;
     mgf* park0;                          // scratch of the first level's size (its own z belongs to the caller)
+    int tab_off[kBottomMax + 1];         // offsets (ints) of each level's index table in shared memory
 };
+
+// index table of one level in shared memory, per (pass i, slot of this CTA): [k0, len, agg(row), col[W], agg(col)[W]]
+__host__ __device__ inline int bottom_tab_stride(int ell_w) { return 3 + 2 * ell_w; }
+__host__ __device__ inline int bottom_passes(int n, int nslots) { return (n + nslots - 1) / nslots; }
 
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -755,19 +766,49 @@ __device__ __forceinline__ Vf<2> ldcg2(const float* p) {
     return r;
 }
 
+template <int LANES>
 __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, int B, const mgf* rhs, mgf* out, int acc,
                                                               const int32_t* __restrict__ n_active, MgParams mp) {
     if (__ldcg(&n_active[1]) == 0) return;                 // uniform over the grid: no CTA is left waiting at a barrier
     constexpr int V = 2;
+    constexpr int U = kBottomU;
+    constexpr int kSlotsCta = kBottomThreads / LANES;                       // rows a CTA works on at a time
+    constexpr int nslots = kBottomCluster * kSlotsCta;
     unsigned rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int cluster = blockIdx.x / kBottomCluster;
-    const int g = (int)rank * kBottomThreads + threadIdx.x;                 // thread index inside the cluster
-    const int lane = g % kBottomLanes, slot = g / kBottomLanes;
-    const int nslots = kBottomCluster * kBottomThreads / kBottomLanes;
-    const int b = (cluster * kBottomLanes + lane) * V;
-    const bool live = b < B;
+    const int lane = threadIdx.x % LANES, sl = threadIdx.x / LANES;         // slot inside the CTA
+    const int slot = (int)rank * kSlotsCta + sl;                            // slot inside the cluster
+    const int b = (cluster * LANES + lane) * V;
+    const bool live = b < B && sl < kSlotsCta;             // LANES need not divide the CTA: the last few threads only synchronise
     const size_t sB = (size_t)B;
+    extern __shared__ float sbot[];                        // [n_coarsest][3][LANES][2] floats, then the index tables
+    int* const tab = reinterpret_cast<int*>(sbot + (size_t)a.n_coarsest * 3 * LANES * 2);
+
+    // ---- index tables of this CTA's rows ------------------------------------------------------------------
+    for (int k = 0; k < a.count; ++k) {
+        const MgMat& A = a.A[k];
+        const MgLevelDev& L = a.L[k];
+        const int W = A.ell_w, stride = bottom_tab_stride(W), passes = bottom_passes(A.n, nslots);
+        int* tk = tab + a.tab_off[k];
+        for (int idx = threadIdx.x; idx < passes * kSlotsCta * (W + 1); idx += kBottomThreads) {
+            int u = idx % (W + 1), rs = idx / (W + 1);                      // rs = pass * kSlotsCta + slot of the CTA
+            int f = (rs / kSlotsCta) * nslots + (int)rank * kSlotsCta + rs % kSlotsCta;
+            if (f >= A.n) continue;
+            int* e = tk + (size_t)rs * stride;
+            if (u == W) {
+                int k0 = A.rowptr[f];
+                e[0] = k0;
+                e[1] = A.rowptr[f + 1] - k0;
+                e[2] = L.agg[f];
+            } else {
+                int col = A.ell_col[(size_t)f * W + u];
+                e[3 + u] = col;
+                e[3 + W + u] = (col >= 0 && col < A.n) ? L.agg[col] : 0;   // padding slots are never used
+            }
+        }
+    }
+    __syncthreads();
 
     // ---- down: t = (K D^-1) rhs, coarse right-hand side = restricted smoothed residual -------------------
     // two sub-stages per level, so that no thread walks an aggregate's members through a chain of dependent loads:
@@ -778,23 +819,28 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
         const MgLevelDev& L = a.L[k];
         const mgf* bv = k == 0 ? rhs : a.b[k];
         mgf* park = k == 0 ? a.park0 : a.z[k];
+        const int W = A.ell_w, stride = bottom_tab_stride(W);
+        const int* tk = tab + a.tab_off[k];
         if (live) {
-            for (int f = slot; f < A.n; f += nslots) {
-                int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+            int pass = 0;
+            for (int f = slot; f < A.n; f += nslots, ++pass) {
+                const int* e = tk + (size_t)(pass * kSlotsCta + sl) * stride;
+                const int k0 = e[0], len = e[1];
+                size_t o = (size_t)f * 3 * sB + b;
+                Vf<V> bc[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) bc[c] = ldcg2(bv + o + c * sB);
                 Vf<V> acc3[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) acc3[c].v[0] = acc3[c].v[1] = 0.0f;
-                constexpr int U = 5;
                 for (int u0 = 0; u0 < len; u0 += U) {
-                    int col[U];
                     Vf<V> w[U], x0[U], x1[U], x2[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) col[u] = A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)];
-#pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (u0 + u < len) w[u] = ldv<V>(A.vals_s + (size_t)(k0 + u0 + u) * sB + b);
-                        else w[u].v[0] = w[u].v[1] = 0.0f;
-                        const mgf* xj = bv + (size_t)col[u] * 3 * sB + b;
+                        int uu = min(u0 + u, len - 1);
+                        w[u] = ldv<V>(A.vals_s + (size_t)(k0 + uu) * sB + b);
+                        if (u0 + u >= len) w[u].v[0] = w[u].v[1] = 0.0f;
+                        const mgf* xj = bv + (size_t)e[3 + uu] * 3 * sB + b;
                         x0[u] = ldcg2(xj);
                         x1[u] = ldcg2(xj + sB);
                         x2[u] = ldcg2(xj + 2 * sB);
@@ -808,13 +854,12 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
                             acc3[2].v[v] += w[u].v[v] * x2[u].v[v];
                         }
                 }
-                size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     stv<V>(a.t[k] + o + c * sB, acc3[c]);
-                    Vf<V> bc = ldcg2(bv + o + c * sB), res;
+                    Vf<V> res;
 #pragma unroll
-                    for (int v = 0; v < V; ++v) res.v[v] = bc.v[v] - mp.omega * acc3[c].v[v];
+                    for (int v = 0; v < V; ++v) res.v[v] = bc[c].v[v] - mp.omega * acc3[c].v[v];
                     stv<V>(park + o + c * sB, res);
                 }
             }
@@ -846,10 +891,9 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
         const int n = a.n_coarsest;
         const mgf* bv = a.b[a.count];
         mgf* e = a.z[a.count];
-        extern __shared__ float sbot[];                    // [n][3][kBottomLanes][2]
-        const int b_first = cluster * kBottomLanes * V;
-        for (int idx = threadIdx.x; idx < n * 3 * kBottomLanes; idx += kBottomThreads) {
-            int ln = idx % kBottomLanes, jc = idx / kBottomLanes;
+        const int b_first = cluster * LANES * V;
+        for (int idx = threadIdx.x; idx < n * 3 * LANES; idx += kBottomThreads) {
+            int ln = idx % LANES, jc = idx / LANES;
             int bb = b_first + ln * V;
             Vf<V> val;
             val.v[0] = val.v[1] = 0.0f;
@@ -861,23 +905,23 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
         if (live) {
             for (int i = slot; i < n; i += nslots) {
                 float s0[2] = {0.0f, 0.0f}, s1[2] = {0.0f, 0.0f}, s2[2] = {0.0f, 0.0f};
-                constexpr int U = 14;
+                constexpr int UC = 14;
                 const size_t stride = (size_t)n * sB;
-                for (int j0 = 0; j0 < n; j0 += U) {
-                    Vf<V> w[U];
+                for (int j0 = 0; j0 < n; j0 += UC) {
+                    Vf<V> w[UC];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                    for (int u = 0; u < UC; ++u) {
                         w[u] = ldv<V>(a.inv + (size_t)min(j0 + u, n - 1) * stride + (size_t)i * sB + b);
                         if (j0 + u >= n) w[u].v[0] = w[u].v[1] = 0.0f;
                     }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float* sj = sbot + ((size_t)(min(j0 + u, n - 1) * 3) * kBottomLanes + lane) * 2;
+                    for (int u = 0; u < UC; ++u) {
+                        const float* sj = sbot + ((size_t)(min(j0 + u, n - 1) * 3) * LANES + lane) * 2;
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
                             s0[v] += w[u].v[v] * sj[v];
-                            s1[v] += w[u].v[v] * sj[kBottomLanes * 2 + v];
-                            s2[v] += w[u].v[v] * sj[2 * kBottomLanes * 2 + v];
+                            s1[v] += w[u].v[v] * sj[LANES * 2 + v];
+                            s2[v] += w[u].v[v] * sj[2 * LANES * 2 + v];
                         }
                     }
                 }
@@ -894,27 +938,39 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
     // ---- up: z = x' + w D^-1 (b - K x'), x' = w D^-1 b + s P e ------------------------------------------------
     for (int k = a.count - 1; k >= 0; --k) {
         const MgMat& A = a.A[k];
-        const MgLevelDev& L = a.L[k];
         const mgf* bv = k == 0 ? rhs : a.b[k];
         const mgf* ec = a.z[k + 1];
         mgf* zo = k == 0 ? out : a.z[k];
+        const int W = A.ell_w, stride = bottom_tab_stride(W);
+        const int* tk = tab + a.tab_off[k];
         if (live) {
-            for (int f = slot; f < A.n; f += nslots) {
-                int k0 = A.rowptr[f], len = A.rowptr[f + 1] - k0;
+            int pass = 0;
+            for (int f = slot; f < A.n; f += nslots, ++pass) {
+                const int* e = tk + (size_t)(pass * kSlotsCta + sl) * stride;
+                const int k0 = e[0], len = e[1];
+                size_t o = (size_t)f * 3 * sB + b;
+                Vf<V> wd = ldv<V>(A.dinv + (size_t)f * sB + b);
+                const mgf* ei = ec + (size_t)e[2] * 3 * sB + b;
+                Vf<V> bc[3], tc[3], e1[3], prev[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    bc[c] = ldcg2(bv + o + c * sB);
+                    tc[c] = ldcg2(a.t[k] + o + c * sB);
+                    e1[c] = ldcg2(ei + c * sB);
+                    if (k == 0 && acc) prev[c] = ldcg2(zo + o + c * sB);
+                    else prev[c].v[0] = prev[c].v[1] = 0.0f;
+                }
                 Vf<V> sacc[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) sacc[c].v[0] = sacc[c].v[1] = 0.0f;
-                constexpr int U = 5;
                 for (int u0 = 0; u0 < len; u0 += U) {
-                    int cg[U];
                     Vf<V> w[U], x0[U], x1[U], x2[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) cg[u] = L.agg[A.ell_col[(size_t)f * A.ell_w + min(u0 + u, len - 1)]];
-#pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (u0 + u < len) w[u] = ldv<V>(A.vals + (size_t)(k0 + u0 + u) * sB + b);
-                        else w[u].v[0] = w[u].v[1] = 0.0f;
-                        const mgf* ej = ec + (size_t)cg[u] * 3 * sB + b;
+                        int uu = min(u0 + u, len - 1);
+                        w[u] = ldv<V>(A.vals + (size_t)(k0 + uu) * sB + b);
+                        if (u0 + u >= len) w[u].v[0] = w[u].v[1] = 0.0f;
+                        const mgf* ej = ec + (size_t)e[3 + W + uu] * 3 * sB + b;
                         x0[u] = ldcg2(ej);
                         x1[u] = ldcg2(ej + sB);
                         x2[u] = ldcg2(ej + 2 * sB);
@@ -928,22 +984,14 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
                             sacc[2].v[v] += w[u].v[v] * x2[u].v[v];
                         }
                 }
-                Vf<V> wd = ldv<V>(A.dinv + (size_t)f * sB + b);
-                const mgf* ei = ec + (size_t)L.agg[f] * 3 * sB + b;
-                size_t o = (size_t)f * 3 * sB + b;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    Vf<V> bc = ldcg2(bv + o + c * sB), tc = ldcg2(a.t[k] + o + c * sB), e1 = ldcg2(ei + c * sB), zc;
+                    Vf<V> zc;
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         float w1 = mp.omega * wd.v[v];
-                        float xn = w1 * bc.v[v] + mp.over * e1.v[v];
-                        zc.v[v] = xn + w1 * (bc.v[v] - mp.omega * tc.v[v] - mp.over * sacc[c].v[v]);
-                    }
-                    if (k == 0 && acc) {
-                        Vf<V> prev = ldcg2(zo + o + c * sB);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) zc.v[v] += prev.v[v];
+                        float xn = w1 * bc[c].v[v] + mp.over * e1[c].v[v];
+                        zc.v[v] = xn + w1 * (bc[c].v[v] - mp.omega * tc[c].v[v] - mp.over * sacc[c].v[v]) + prev[c].v[v];
                     }
                     stv<V>(zo + o + c * sB, zc);
                 }
@@ -1552,10 +1600,16 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
     const MgLevelDev& C = M.lv[nl - 1];
     if (w.mg.inv) {
         size_t smem = sizeof(double) * ((size_t)C.n * C.n + 2 * (size_t)C.n);
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            DFDM_CUDA_OK(cudaFuncSetAttribute(k_mg_coarsest_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        if (smem > 48 * 1024) {                           // opt-in is per device and per function
+            static std::mutex mu;
+            static std::map<int, size_t> configured;
+            int dev = 0;
+            DFDM_CUDA_OK(cudaGetDevice(&dev));
+            std::lock_guard<std::mutex> lock(mu);
+            if (configured[dev] < smem) {
+                DFDM_CUDA_OK(cudaFuncSetAttribute(k_mg_coarsest_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = smem;
+            }
         }
         k_mg_coarsest_invert<<<B, 256, smem, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.inv);
         DFDM_LAUNCH_OK("k_mg_coarsest_invert");
@@ -1633,12 +1687,46 @@ static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
     a.n_coarsest = M.lv[nl - 1].n;
     a.inv = w.mg.inv;
     a.park0 = w.mg.r2[l0];                                   // free here: the bottom levels are never W levels
-    const int pairs = c.B / 2;
-    const int nclusters = (pairs + kBottomLanes - 1) / kBottomLanes;
+    const int pairs = (c.B + 1) / 2;
+    // fewer design pairs per cluster = more clusters = shorter per-thread chains, as long as the clusters are co-resident
+    static const int forced_lanes = tile_factor("DFDM_BOTTOM_LANES", 0);
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // at most 15 clusters of 8 CTAs x 512 threads are co-resident on a B200 (launch__cluster_max_active)
+    const int max_clusters = sms / kBottomCluster - 3;
+    int lanes = 16;
+    if ((pairs + 7) / 8 <= max_clusters) lanes = 8;       // (10 or 12 pairs per cluster measured the same as 16 at batch 256)
+    if (forced_lanes == 8 || forced_lanes == 16) lanes = forced_lanes;
+    const int nclusters = (pairs + lanes - 1) / lanes;
+    const int nslots = kBottomCluster * (kBottomThreads / lanes);
+    int tab = 0;
+    for (int k = 0; k < a.count; ++k) {
+        a.tab_off[k] = tab;
+        tab += bottom_passes(a.A[k].n, nslots) * (kBottomThreads / lanes) * bottom_tab_stride(a.A[k].ell_w);
+    }
+    a.tab_off[a.count] = tab;
+    const size_t smem = sizeof(float) * (size_t)a.n_coarsest * 3 * lanes * 2 + sizeof(int) * (size_t)tab;
+    auto kernel = lanes == 8 ? k_mg_bottom<8> : k_mg_bottom<16>;
+    if (smem > 48 * 1024) {
+        static std::mutex mu;
+        static std::map<std::pair<int, int>, size_t> configured;
+        int dev = 0;
+        DFDM_CUDA_OK(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[{dev, lanes}];
+        if (have < smem) {
+            DFDM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(nclusters * kBottomCluster));
     cfg.blockDim = dim3(kBottomThreads);
-    cfg.dynamicSmemBytes = sizeof(float) * (size_t)a.n_coarsest * 3 * kBottomLanes * 2;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = c.st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1647,7 +1735,7 @@ static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mg_bottom, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp));
+    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp));
     DFDM_LAUNCH_OK("k_mg_bottom");
     return DFDM_OK;
 }
