@@ -339,6 +339,8 @@ def gpu_arm(args, rank, world, local_rank):
                "k_mg_down[level 0]": (4.0 * nnz + 36.0 * nf + 12.0 * nc) * batch,
                # K (4 nnz), r (24 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
                "k_mg_up[level 0]": (4.0 * nnz + 52.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
+        if is_mg:
+            alg["multigrid coarse levels (per V-cycle)"] = coarse_cycle_bytes(plan, args.mg_w_levels) * batch
         kernels = []
         for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction", "k_mg_down[level 0]", "k_mg_up[level 0]",
                                   "multigrid coarse levels (per V-cycle)")):
@@ -351,6 +353,12 @@ def gpu_arm(args, rank, world, local_rank):
                             "frac": top["achieved_gbs"] / peak, "traffic": traffic_for(top["kernel"], wl["name"]),
                             "peak_source": peak_src, "timing": "CUDA events on the launch stream after every PCG launch, timed region"}
         line["kernels"] = kernels
+        it_ms = sum(kk["avg_ms"] for kk in kernels)
+        it_bytes = sum(kk["algorithmic_bytes"] for kk in kernels)
+        line["roofline"]["iteration"] = {"what": "one whole PCG iteration = all the kernels listed under 'kernels'", "ms": it_ms,
+                                         "algorithmic_bytes": it_bytes, "achieved": it_bytes / (it_ms * 1e-3) / 1e9,
+                                         "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak, "share_of_step": sum(kk["share_of_step"] for kk in kernels)}
+        line["roofline"]["frac_of_nominal_8000"] = top["achieved_gbs"] / 8000.0
     else:
         # direct path: one fused kernel per step; mandatory I/O only (q in, loss + dq out)
         alg = batch * (16.0 * E + 8.0)
@@ -359,9 +367,59 @@ def gpu_arm(args, rank, world, local_rank):
                             "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic_for("k_direct_eval", wl["name"]),
                             "peak_source": peak_src,
                             "note": "shared-memory factorisation: latency / FP64-issue bound, not HBM bound; fraction reported for completeness"}
+        # FP64 view of the same kernel: banded LDL^T nf*w*(w+2) flops, two solves x 3 right-hand sides x (4 nf w + nf)
+        w_band = plan.info["bandwidth_solver"]
+        flops = batch * (nf * w_band * (w_band + 2.0) + 6.0 * (4.0 * nf * w_band + nf))
+        dgemm = fp64_peak_gflops(device)
+        line["roofline"]["fp64"] = {"flops_per_step": flops, "achieved_gflops": flops / (ms * 1e-3) / 1e9, "peak_gflops": dgemm,
+                                    "frac": flops / (ms * 1e-3) / 1e9 / dgemm, "peak_source": "torch.matmul f64 4096^3 on this GPU, best of 5 (calibration only)"}
+        line["roofline"]["frac_of_nominal_8000"] = alg / (ms * 1e-3) / 1e9 / 8000.0
     if cpu:
         line["cpu_baseline"] = cpu
     return line
+
+
+def fp64_peak_gflops(device):
+    """Measured FP64 GEMM rate of this GPU: the ceiling the banded factorisation is compared with (not part of the path)."""
+    import torch
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    best = float("inf")
+    for _ in range(5):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch.matmul(a, b)
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    return 2.0 * 4096 ** 3 / (best * 1e-3) / 1e9
+
+
+def coarse_cycle_bytes(plan, mg_w_levels):
+    """Algorithmic bytes per design of the levels below level 0 in one preconditioner cycle (single precision):
+    per visit of level l: down 4 nnz + 24 n + 12 n_next, up 4 nnz + 40 n + 12 n_next (+ 12 n when it adds to a previous
+    correction), the W-cycle's residual 4 nnz + 36 n; the coarsest level is a dense product, 4 n^2 + 24 n."""
+    from dfdm_b200 import _lib
+    rows = [int(v) for v in plan.array(_lib.ARR_MG_ROWS)]
+    nnzs = [int(v) for v in plan.array(_lib.ARR_MG_NNZ)]
+    if len(rows) < 2:
+        return 0.0
+    w = 0 if mg_w_levels < 0 else (mg_w_levels or 2)
+    last = len(rows) - 1
+    total, visits = 0.0, 1
+    for l in range(1, last + 1):
+        twice = l <= w
+        visits *= 2 if twice else 1
+        if l == last:
+            total += visits * (4.0 * rows[l] ** 2 + 24.0 * rows[l])
+        else:
+            down = 4.0 * nnzs[l] + 24.0 * rows[l] + 12.0 * rows[l + 1]
+            up = 4.0 * nnzs[l] + 40.0 * rows[l] + 12.0 * rows[l + 1]
+            total += visits * (down + up)
+            if twice:                                   # second visit: residual of the first, correction added to it
+                total += (visits // 2) * (4.0 * nnzs[l] + 36.0 * rows[l] + 12.0 * rows[l])
+    return total
 
 
 def reference_arm(args, rank, world):

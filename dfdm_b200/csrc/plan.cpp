@@ -360,6 +360,14 @@ static void build_pcg_order(Plan& P) {
         colidx = L.colidx;
         P.mg.push_back(std::move(L));
     }
+    if (!P.mg.empty()) {
+        P.mg_rows.push_back(P.nf);
+        P.mg_nnz.push_back(P.nnz);
+        for (const MgLevel& L : P.mg) {
+            P.mg_rows.push_back(L.n);
+            P.mg_nnz.push_back(L.nnz);
+        }
+    }
 }
 
 int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fixed, Plan& P) {
@@ -546,6 +554,8 @@ const int32_t* dfdm_plan_array(const dfdm_plan* plan, int32_t which, int64_t* le
         case DFDM_ARR_NODE_INC_PTR: v = &plan->ninc_ptr; break;
         case DFDM_ARR_NODE_INC_EDGE: v = &plan->ninc_edge; break;
         case DFDM_ARR_NODE_INC_SIGN: v = &plan->ninc_sign; break;
+        case DFDM_ARR_MG_ROWS: v = &plan->mg_rows; break;
+        case DFDM_ARR_MG_NNZ: v = &plan->mg_nnz; break;
         default: dfdm::set_error("dfdm_plan_array: unknown array id"); return nullptr;
     }
     if (length) *length = (int64_t)v->size();

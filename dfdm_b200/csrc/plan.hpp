@@ -93,6 +93,7 @@ struct Plan {
     RowSet pg;                            // rows in the PCG path's own (hierarchical, locality preserving) order
     std::vector<int32_t> pg_perm;         // [nf] free index of each PCG row
     std::vector<MgLevel> mg;              // coarse levels, finest first (built on the PCG row order)
+    std::vector<int32_t> mg_rows, mg_nnz; // sizes of level 0 .. coarsest, for reporting (DFDM_ARR_MG_ROWS / _NNZ)
     mutable std::map<int, MgDev> mg_dev;
 
     // lazily created device mirrors and cached arenas for the *_host entry points

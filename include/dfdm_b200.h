@@ -98,6 +98,8 @@ typedef struct dfdm_plan_info {
 #define DFDM_ARR_NODE_INC_PTR 7  /* int32[n+1]  node -> incident edges */
 #define DFDM_ARR_NODE_INC_EDGE 8 /* int32[2E] */
 #define DFDM_ARR_NODE_INC_SIGN 9 /* int32[2E]: C[e, node] = -1 (tail u) or +1 (head v); model.py:23,34 */
+#define DFDM_ARR_MG_ROWS 10      /* int32[mg_levels+1]: rows of every multigrid level, level 0 = n_free (empty without a hierarchy) */
+#define DFDM_ARR_MG_NNZ 11       /* int32[mg_levels+1]: stored entries of every level's operator */
 
 DFDM_API const char* dfdm_last_error(void);
 DFDM_API int32_t dfdm_abi_version(void);

@@ -95,6 +95,13 @@ def test_large_grid_plan_counts():
     plan = Plan(len(fixed), edges, fixed)
     assert (plan.n, plan.n_edges, plan.n_free, plan.n_fixed, plan.nnz) == (66564, 132612, 65536, 1028, 326656)
     assert plan.auto_solver == "pcg"
+    # the multigrid hierarchy of the plan: every level about a quarter of the one above, dense solve at the bottom
+    rows, nnzs = plan.array(_lib.ARR_MG_ROWS), plan.array(_lib.ARR_MG_NNZ)
+    assert len(rows) == plan.info["mg_levels"] + 1 == len(nnzs)
+    assert rows[0] == plan.n_free and nnzs[0] == plan.nnz
+    assert rows[1] == plan.info["mg_n_coarse"] and rows[-1] == plan.info["mg_n_coarsest"] <= 96
+    assert all(3.0 < rows[k] / rows[k + 1] <= 4.0 for k in range(len(rows) - 1))
+    assert all(nnzs[k] >= rows[k] for k in range(len(rows)))
 
 
 def test_bad_arguments_are_rejected():
