@@ -10,7 +10,7 @@ import pytest
 from cases import golden_cases, case_arrays, oracle_terms, program_inputs, goal_objects, constraint_objects
 from oracle import fdm_oracle as O
 from dfdm_b200.datastructures import FDNetwork
-from dfdm_b200.equilibrium import EquilibriumModel, EquilibriumState, network_updated
+from dfdm_b200.equilibrium import EquilibriumModel, EquilibriumState, NetworkBatch, network_updated
 from dfdm_b200.goals import goals_state
 from dfdm_b200.losses import Loss
 from dfdm_b200.optimization import OptimizationRecorder
@@ -136,6 +136,28 @@ def test_network_update_writes_state_into_a_copy():
         assert new.node_residual(node) == g["residuals"][idx].tolist()
     assert abs(new.loadpath() - np.sum(np.abs(g["forces"] * g["lengths"]))) < 1e-9
     assert net.node_coordinates(24) != new.node_coordinates(24)
+
+
+def test_network_batch_defers_the_write_back():
+    """A batch of states materialises networks only for the designs asked for (row f-3: lazy write-back)."""
+    case = CASES["pillow"]
+    g, eqstate = _golden_state("pillow")
+    scale = np.array([1.0, 2.0, 0.5])
+    batched = EquilibriumState(*[np.stack([np.asarray(a) * s for s in scale]) for a in
+                                 (eqstate.xyz, eqstate.residuals, eqstate.vectors, eqstate.lengths, eqstate.forces, eqstate.force_densities)])
+    batch = NetworkBatch(case["network"], batched)
+    assert len(batch) == 3 and not batch._made
+    second = batch[1]
+    assert list(batch._made) == [1] and batch[1] is second and batch[-2] is second
+    for idx, edge in second.index_uv().items():
+        assert second.edge_attribute(edge, "length") == 2.0 * g["lengths"][idx]
+    assert np.allclose(batch.loadpaths(), scale ** 2 * np.sum(np.abs(g["forces"] * g["lengths"])), rtol=1e-14)
+    assert abs(batch[2].loadpath() - batch.loadpaths()[2]) < 1e-9
+    assert len(batch[0:2]) == 2
+    with pytest.raises(IndexError):
+        batch[3]
+    with pytest.raises(ValueError):
+        NetworkBatch(case["network"], eqstate)
 
 
 def test_recorder_round_trip(tmp_path):

@@ -47,6 +47,25 @@ def test_fdm_updates_a_copy_of_the_network(name):
     assert abs(eq.loadpath() - np.sum(np.abs(g["forces"] * g["lengths"]))) < 1e-9 * max(1.0, eq.loadpath())
 
 
+def test_fdm_batch_equals_fdm_design_by_design():
+    from dfdm_b200.equilibrium import fdm_batch
+    case = CASES["dome"]
+    g = np.load(os.path.join(GOLDEN, "dome.npz"))
+    net = case["network"].copy()
+    q = np.stack([g["q"], 1.1 * g["q"], 0.9 * g["q"]])
+    batch = fdm_batch(net, q)
+    assert len(batch) == 3
+    for b in (0, 2):
+        one = net.copy()
+        for edge, value in zip(list(one.edges()), q[b]):
+            one.edge_forcedensity(edge, float(value))
+        eq = fdm(one)
+        assert _rel([batch[b].node_coordinates(k) for k in net.nodes()], [eq.node_coordinates(k) for k in net.nodes()]) < 1e-12
+        assert _rel(batch[b].edges_forces(), eq.edges_forces()) < 1e-12
+    assert _rel([batch[0].node_coordinates(k) for k in net.nodes()], g["xyz"]) < 1e-9
+    assert _rel(batch.loadpaths()[0], np.sum(np.abs(g["forces"] * g["lengths"]))) < 1e-9
+
+
 @pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if c["terms"]))
 def test_loss_objects_match_reference(name):
     case = CASES[name]
