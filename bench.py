@@ -341,9 +341,12 @@ def gpu_arm(args, rank, world, local_rank):
                "k_mg_up[level 0]": (4.0 * nnz + 52.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
         if is_mg:
             alg["multigrid coarse levels (per V-cycle)"] = coarse_cycle_bytes(plan, args.mg_w_levels) * batch
+        alg["k_assemble"] = (8.0 * E + 8.0 * nnz + 32.0 * nf) * batch      # q in; K values, 1/diag, b (3 columns) out
+        # k_positions 48 n; k_edge_state 48 E + 24 n; k_node_state 32 E + 96 n; k_edge_adjoint 80 E + 24 n; k_adjoint_rhs 24 E + 48 n
+        alg["state, loss and reverse edge kernels (5 launches)"] = (184.0 * E + 240.0 * plan.n) * batch
         kernels = []
         for k, name in enumerate(("k_pcg_spmv", "k_pcg_update", "k_pcg_direction", "k_mg_down[level 0]", "k_mg_up[level 0]",
-                                  "multigrid coarse levels (per V-cycle)")):
+                                  "multigrid coarse levels (per V-cycle)", "k_assemble", "state, loss and reverse edge kernels (5 launches)")):
             if prof_count[k]:
                 avg_ms = prof_ms[k] / prof_count[k]
                 kernels.append({"kernel": name, "launches": prof_count[k], "avg_ms": avg_ms, "share_of_step": prof_ms[k] / ms_total,
@@ -354,11 +357,13 @@ def gpu_arm(args, rank, world, local_rank):
                             "frac": top["achieved_gbs"] / peak, "traffic": traffic_for(top["kernel"], wl["name"]),
                             "peak_source": peak_src, "timing": "CUDA events on the launch stream after every PCG launch, timed region"}
         line["kernels"] = kernels
-        it_ms = sum(kk["avg_ms"] for kk in kernels)
-        it_bytes = sum(kk["algorithmic_bytes"] for kk in kernels)
-        line["roofline"]["iteration"] = {"what": "one whole PCG iteration = all the kernels listed under 'kernels'", "ms": it_ms,
+        once = ("k_assemble", "state, loss and reverse edge kernels (5 launches)")      # these run once per evaluation
+        per_iteration = [kk for kk in kernels if kk["kernel"] not in once]
+        it_ms = sum(kk["avg_ms"] for kk in per_iteration)
+        it_bytes = sum(kk["algorithmic_bytes"] for kk in per_iteration)
+        line["roofline"]["iteration"] = {"what": "one whole PCG iteration = the kernels listed under 'kernels' except k_assemble and the state / loss group", "ms": it_ms,
                                          "algorithmic_bytes": it_bytes, "achieved": it_bytes / (it_ms * 1e-3) / 1e9,
-                                         "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak, "share_of_step": sum(kk["share_of_step"] for kk in kernels)}
+                                         "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak, "share_of_step": sum(kk["share_of_step"] for kk in per_iteration)}
         line["roofline"]["frac_of_nominal_8000"] = top["achieved_gbs"] / 8000.0
     else:
         # direct path: one fused kernel per step; mandatory I/O only (q in, loss + dq out)

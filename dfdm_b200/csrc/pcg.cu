@@ -144,30 +144,43 @@ __global__ void __launch_bounds__(kThreads) k_assemble(PlanDev P, LaneCfg cfg, i
                                                       double* __restrict__ vals, double* __restrict__ dinv, double* __restrict__ rhs) {
     LANE_SETUP();
     if (!live) return;
+    constexpr int U = 4;                                   // incidences in flight: a grid node has at most 4
     for (int f = row0; f < P.nf; f += rstride) {
         int node = P.free_nodes[f];
         double diag = 0.0;
         double r0 = loads[node * 3 + 0], r1 = loads[node * 3 + 1], r2 = loads[node * 3 + 2];
         int k0 = P.finc_ptr[f], k1 = P.finc_ptr[f + 1];
+        int dslot = P.diagslot[f];
         int prev = -1;
         double acc = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            double qe = qT[(size_t)P.finc_edge[k] * B + b];
-            int code = P.finc_code[k];
-            diag += qe;
-            if (code >= 0) {
-                // entries of one row are grouped by slot only for multi-edges; accumulate through memory then
-                if (code == prev) acc += -qe; else acc = -qe;
-                vals[(size_t)code * B + b] = acc;
-                prev = code;
-            } else {
-                const double* xk = xfix + (size_t)(-1 - code) * 3;
-                r0 += qe * xk[0];
-                r1 += qe * xk[1];
-                r2 += qe * xk[2];
+        for (int kb = k0; kb < k1; kb += U) {
+            int code[U];
+            double qv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                  // index loads first, then the q gathers, then the arithmetic
+                int k = min(kb + u, k1 - 1);
+                code[u] = P.finc_code[k];
+                qv[u] = qT[(size_t)P.finc_edge[k] * B + b];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (kb + u >= k1) break;
+                double qe = qv[u];
+                diag += qe;
+                if (code[u] >= 0) {
+                    // entries of one row are grouped by slot only for multi-edges; accumulate through memory then
+                    if (code[u] == prev) acc += -qe; else acc = -qe;
+                    vals[(size_t)code[u] * B + b] = acc;
+                    prev = code[u];
+                } else {
+                    const double* xk = xfix + (size_t)(-1 - code[u]) * 3;
+                    r0 += qe * xk[0];
+                    r1 += qe * xk[1];
+                    r2 += qe * xk[2];
+                }
             }
         }
-        vals[(size_t)P.diagslot[f] * B + b] = diag;
+        vals[(size_t)dslot * B + b] = diag;
         dinv[(size_t)f * B + b] = 1.0 / diag;
         rhs[((size_t)f * 3 + 0) * B + b] = r0;
         rhs[((size_t)f * 3 + 1) * B + b] = r1;
@@ -1276,21 +1289,23 @@ __global__ void __launch_bounds__(kThreads) k_edge_adjoint(PlanDev P, GoalProgDe
             for (int c = 0; c < 3; ++c) u[c] = U[((size_t)e * 3 + c) * B + b];
             double len = Lg[(size_t)e * B + b], f = F[(size_t)e * B + b], qe = qT[(size_t)e * B + b];
             double ub[3] = {0, 0, 0}, lb = 0.0, fb = 0.0;
+            double g[3] = {0, 0, 0};
+            if (seeds) {                                   // every load of the edge is issued before the goal arithmetic
+                int un = P.edges[2 * e], vn = P.edges[2 * e + 1];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c] = Rb[((size_t)vn * 3 + c) * B + b] - Rb[((size_t)un * 3 + c) * B + b];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (cU) ub[c] = cU[((size_t)e * 3 + c) * B + b];
+                if (cL) lb = cL[(size_t)e * B + b];
+                if (cF) fb = cF[(size_t)e * B + b];
+            }
             if (has_prog) {
                 int g0 = G.egoal_ptr[e], g1 = G.egoal_ptr[e + 1];
                 if (g1 > g0) loss += edge_goals(G.recs, g0, g1, u, len, f, ub, lb, fb);
                 loss += G.l2_alpha * qe * qe;
             }
             if (seeds) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (cU) ub[c] += cU[((size_t)e * 3 + c) * B + b];
-                if (cL) lb += cL[(size_t)e * B + b];
-                if (cF) fb += cF[(size_t)e * B + b];
-                int un = P.edges[2 * e], vn = P.edges[2 * e + 1];
-                double g[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) g[c] = Rb[((size_t)vn * 3 + c) * B + b] - Rb[((size_t)un * 3 + c) * B + b];
                 double d = edge_adjoint(qe, u, len, f, g, lpb, ub, lb, fb);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) Ub[((size_t)e * 3 + c) * B + b] = ub[c];
@@ -1941,8 +1956,17 @@ int run_pcg(Eval& ev) {
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.tickets, 0, sizeof(int32_t) * (size_t)(cfg.nchunks + 1), st));
     rc = to_interleaved(ev.q, w.qT, B, P.E, st);
     if (rc) return rc;
-    k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
-    DFDM_LAUNCH_OK("k_assemble");
+    {
+        size_t used = 0;
+        prof_mark(st, -1, used);
+        k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
+        DFDM_LAUNCH_OK("k_assemble");
+        prof_mark(st, 6, used);
+        if (used) {                                       // profiling only: the solver's polls reuse these events
+            DFDM_CUDA_OK(cudaStreamSynchronize(st));
+            prof_resolve(used);
+        }
+    }
     g_iters[0] = g_iters[1] = 0;
     if (use_mg) {
         rc = mg_setup(P, ev.M, cfg, B, w, st);
@@ -1957,6 +1981,8 @@ int run_pcg(Eval& ev) {
 
     const bool net = ev.has_prog && ev.G.n_net > 0;
     const bool seeds = ev.adjoint;
+    size_t post_used = 0;
+    prof_mark(st, -1, post_used);
     k_positions<<<grid, kThreads, 0, st>>>(P, cfg, B, w.xs, ev.xfix, w.X);
     DFDM_LAUNCH_OK("k_positions");
     k_edge_state<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, w.X, w.U, w.L, w.F, net ? w.lp_partial : nullptr);
@@ -1988,6 +2014,11 @@ int run_pcg(Eval& ev) {
     if (seeds) {
         k_adjoint_rhs<<<grid, kThreads, 0, st>>>(P, cfg, B, w.Xb, w.Ub, w.r);
         DFDM_LAUNCH_OK("k_adjoint_rhs");
+        prof_mark(st, 7, post_used);                       // state, goals / loss and reverse edge passes as one interval
+        if (post_used) {
+            DFDM_CUDA_OK(cudaStreamSynchronize(st));
+            prof_resolve(post_used);
+        }
         rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, st, host_flag, &g_iters[1]);
         if (rc) return rc;
         if (ev.status) {

@@ -219,6 +219,9 @@ DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_
 #define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   8 nnz + 48 n_free + 24 n_coarse */
 #define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          8 nnz + 80 n_free + 24 n_coarse */
 #define DFDM_PROF_MG_COARSE 5  /* all kernels below the finest level, per V-cycle */
+#define DFDM_PROF_ASSEMBLE 6   /* k_assemble: K values, 1/diag and b from q          8 E + 8 nnz + 32 n_free per design */
+#define DFDM_PROF_STATE 7      /* k_positions .. k_adjoint_rhs as one interval (loss_and_grad only): state, goals / loss,
+                                  reverse edge passes                                ~ 184 E + 240 n per design */
 DFDM_API void dfdm_profile_enable(int32_t on);
 DFDM_API void dfdm_profile_read(double* ms /* [8] */, int64_t* count /* [8] */);
 

@@ -343,3 +343,38 @@ def test_pcg_with_force_densities_spanning_orders_of_magnitude(batch):
         assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
     f, a = _lib.last_pcg_iterations()
     assert f < 400 and a < 400           # the multigrid preconditioner holds without the Jacobi fallback
+
+
+def test_multigrid_pcg_on_an_irregular_triangulation():
+    """A Delaunay mesh of 6 000 random points (node degrees 3 ... 12, hull fixed): the aggregation hierarchy built by
+    pairwise matching has to work without any grid structure.  Checked against the sparse CPU oracle."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(21)
+    pts = rng.random((6000, 2))
+    tri = Delaunay(pts)
+    pairs = np.vstack([tri.simplices[:, [0, 1]], tri.simplices[:, [1, 2]], tri.simplices[:, [2, 0]]])
+    edges = np.unique(np.sort(pairs, axis=1), axis=0).astype(np.int32)
+    fixed = np.zeros(len(pts), dtype=np.uint8)
+    fixed[np.unique(tri.convex_hull)] = 1
+    xyz = np.column_stack([pts, 0.2 * np.sin(3.0 * pts[:, 0]) * np.cos(2.0 * pts[:, 1])])
+    loads = np.zeros_like(xyz)
+    loads[:, 2] = -1.0 / len(pts)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.auto_solver == "pcg" and plan.info["mg_levels"] >= 3
+    rows = plan.array(_lib.ARR_MG_ROWS)
+    assert all(rows[k + 1] < 0.5 * rows[k] for k in range(len(rows) - 1))          # coarsening does not stall
+    ev = Evaluator(plan, loads, xyz[plan.fixed])
+    q = 1.0 + 0.8 * (rng.random((4, len(edges))) - 0.5)
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    out = ev.loss_and_grad(prog, q, outputs=("xyz",))
+    assert np.all(out["status"].cpu().numpy() == 0)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    for b in (0, 3):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.1)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+    f, a = _lib.last_pcg_iterations()
+    assert f <= 80 and a <= 80, (f, a)                                             # multigrid, not the Jacobi fallback
