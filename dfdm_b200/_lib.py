@@ -40,7 +40,7 @@ SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan
 class Options(C.Structure):
     _fields_ = [("solver", C.c_int32), ("pcg_maxiter", C.c_int32), ("pcg_rtol", C.c_double),
                 ("pcg_check_every", C.c_int32), ("pcg_precond", C.c_int32), ("mg_omega", C.c_double), ("mg_over", C.c_double),
-                ("mg_w_levels", C.c_int32), ("reserved", C.c_int32)]
+                ("mg_w_levels", C.c_int32), ("reserved", C.c_int32), ("mg_over_w", C.c_double)]
 
 
 class PlanInfo(C.Structure):
@@ -87,7 +87,7 @@ def _load():
     lib.dfdm_profile_read.restype = None
     for name in SYMBOLS:
         getattr(lib, name)
-    if lib.dfdm_abi_version() != 1:
+    if lib.dfdm_abi_version() != 2:
         raise ImportError("dfdm_b200: ABI version mismatch between _lib.py and libdfdm_b200.so")
     return lib
 
@@ -101,13 +101,13 @@ def check(rc):
 
 
 def make_options(solver="auto", pcg_maxiter=0, pcg_rtol=0.0, pcg_check_every=0, pcg_precond="auto", mg_omega=0.0, mg_over=0.0,
-                 mg_w_levels=0):
+                 mg_w_levels=0, mg_over_w=0.0):
     if isinstance(solver, str):
         solver = SOLVERS[solver]
     if isinstance(pcg_precond, str):
         pcg_precond = PRECONDS[pcg_precond]
     return Options(solver, int(pcg_maxiter), float(pcg_rtol), int(pcg_check_every), int(pcg_precond), float(mg_omega), float(mg_over),
-                   int(mg_w_levels), 0)
+                   int(mg_w_levels), 0, float(mg_over_w))
 
 
 def plan_array(handle, which):

@@ -467,7 +467,8 @@ struct MgMat {                 // one level's operator (level 0: the plan's CSR 
 
 constexpr double kMgOmegaDefault = 0.8;
 constexpr double kMgOverDefault = 1.7;   // V-cycle
-constexpr double kMgOverW = 1.3;         // W-cycle: nested scalings multiply, so stay below sqrt(2) (1.5 is faster on grids, 1.7 diverges)
+constexpr double kMgOverW = 1.3;         // under a W-cycle, levels whose coarse problem is solved once: nested scalings multiply (1.7 diverges)
+constexpr double kMgOverTwice = 1.7;     // levels whose coarse problem is solved twice: two corrections combine to 1-(1-s)^2 <= 1, safe below 2
 struct MgParams { float omega, over; };
 
 // level 0: single-precision copies of K, K D^-1 and 1/diag from the assembled double-precision operator
@@ -1651,7 +1652,8 @@ struct MgCtx {
     PcgBuffers* w;
     int B;
     cudaStream_t st;
-    MgParams mp;
+    MgParams mp;           // levels whose coarse problem is solved twice (W): the combined correction never exceeds 1
+    MgParams mp_single;    // levels whose coarse problem is solved once (or exactly): scalings of nested levels multiply
     LaneCfg vbase;
     int w_levels;          // coarse levels 1 .. w_levels are visited twice per visit of their parent (W-cycle)
     int bottom;            // first level handled by the single-launch bottom kernel (0: none)
@@ -1666,20 +1668,21 @@ static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out, const
     const MgDev& M = *c.M;
     PcgBuffers& w = *c.w;
     MgMat A = mg_mat(*c.P, M, w, l);
+    const MgParams mp = l < c.w_levels ? c.mp : c.mp_single;
     LaneCfg cd = rows_cfg(k_mg_down<mgf, V>, c.vbase, M.lv[l].n);
     k_mg_down<mgf, V><<<cd.nchunks * cd.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cd, c.B, rhs, w.mg.t[l], w.mg.b[l + 1],
-                                                                      w.S.n_active + w.S.par, c.mp);
+                                                                      w.S.n_active + w.S.par, mp);
     DFDM_LAUNCH_OK("k_mg_down");
     int rc = mg_solve_level<V>(c, l + 1, w.mg.b[l + 1], w.mg.z[l + 1]);
     if (rc) return rc;
     if (acc) {
         LaneCfg cu = rows_cfg(k_mg_up<mgf, V, true>, c.vbase, A.n);
         k_mg_up<mgf, V, true><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
-                                                                              0, 0, c.mp);
+                                                                              0, 0, mp);
     } else {
         LaneCfg cu = rows_cfg(k_mg_up<mgf, V, false>, c.vbase, A.n);
         k_mg_up<mgf, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
-                                                                               0, 0, c.mp);
+                                                                               0, 0, mp);
     }
     DFDM_LAUNCH_OK("k_mg_up");
     return DFDM_OK;
@@ -1750,7 +1753,7 @@ static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp));
+    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp_single));
     DFDM_LAUNCH_OK("k_mg_bottom");
     return DFDM_OK;
 }
@@ -1791,7 +1794,7 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
 
 template <int V>
 static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, int first, cudaStream_t st, size_t& used,
-                       MgParams mp, int w_levels) {
+                       MgParams mp, float over_w, int w_levels) {
     static const int down_tiles = tile_factor("DFDM_TILE_DOWN", 1), up_tiles = tile_factor("DFDM_TILE_UP", 4);
     // the bottom kernel takes over at the first level with few rows, below the W levels, when the coarsest inverse is dense
     static const int bottom_rows = tile_factor("DFDM_MG_BOTTOM", 24) * 64;
@@ -1800,7 +1803,9 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
         for (int l = std::max(1, w_levels + 1); l < M.n_levels; ++l)
             if (M.lv[l - 1].n <= bottom_rows && M.n_levels - l <= kBottomMax) { bottom = l; break; }
     }
-    MgCtx c{&P, &M, &w, B, st, mp, vec_base(B, V), w_levels, bottom};
+    MgParams mpw = mp;
+    mpw.over = over_w;
+    MgCtx c{&P, &M, &w, B, st, mpw, mp, vec_base(B, V), w_levels, bottom};
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     MgMat A = mg_mat(P, M, w, 0);
     LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
@@ -1812,8 +1817,9 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     if (rc) return rc;
     prof_mark(st, 5, used);                              // everything below the finest level, per cycle
     LaneCfg cu = rows_cfg(k_mg_up<double, V, false>, c.vbase, A.n, up_tiles);
+    const MgParams mp0 = w_levels > 0 ? mpw : mp;     // level 1 is solved twice whenever there is a W level
     k_mg_up<double, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, st>>>(A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0],
-                                                                          w.S, 1, first, mp);
+                                                                          w.S, 1, first, mp0);
     DFDM_LAUNCH_OK("k_mg_up");
     prof_mark(st, 4, used);
     return DFDM_OK;
@@ -1821,10 +1827,10 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
 
 // z[0] = M r for all designs; the last kernel also reduces rho' = r . z and sets beta
 static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, int first, cudaStream_t st,
-                     size_t& used, MgParams mp, int w_levels) {
+                     size_t& used, MgParams mp, float over_w, int w_levels) {
     (void)base;
-    return (B % 2 == 0) ? mg_vcycle_v<2>(P, M, B, w, first, st, used, mp, w_levels)
-                        : mg_vcycle_v<1>(P, M, B, w, first, st, used, mp, w_levels);
+    return (B % 2 == 0) ? mg_vcycle_v<2>(P, M, B, w, first, st, used, mp, over_w, w_levels)
+                        : mg_vcycle_v<1>(P, M, B, w, first, st, used, mp, over_w, w_levels);
 }
 
 static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
@@ -1868,51 +1874,99 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
     if (iter_cap > 0) maxiter = std::min(maxiter, iter_cap);
     double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
-    int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : (mg ? 5 : 25);
+    const int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : 0;       // 0: look-ahead polls (below)
+    const float over_w = (float)(opt.mg_over_w > 0 ? opt.mg_over_w : (w_levels > 0 ? kMgOverTwice : (double)mp.over));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
     w.S.par = 0;
     k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0);
     DFDM_LAUNCH_OK("k_pcg_init");
-    size_t used0 = 0;
+    size_t used = 0;
     if (mg) {
-        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used0, mp, w_levels);              // z = M r, rho = r.z, beta = 0
+        int rc = mg_vcycle(P, *M, base, B, w, 1, st, used, mp, over_w, w_levels);   // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
         k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
                                                                                    w.S, 0);
         DFDM_LAUNCH_OK("k_pcg_direction");
         w.S.par ^= 1;
     }
-    int it = 0;
-    while (it < maxiter) {
-        int stop = std::min(maxiter, it + every);
-        size_t used = 0;
-        prof_mark(st, -1, used);
-        for (; it < stop; ++it) {
-            k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
-            DFDM_LAUNCH_OK("k_pcg_spmv");
-            prof_mark(st, 0, used);
-            k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
-                                                                                    mg ? 1 : 0);
-            DFDM_LAUNCH_OK("k_pcg_update");
-            prof_mark(st, 1, used);
-            if (mg) {
-                int rc = mg_vcycle(P, *M, base, B, w, 0, st, used, mp, w_levels);
-                if (rc) return rc;
-                prof_mark(st, -1, used);
-            }
-            k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r,
-                                                                                       mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1);
-            DFDM_LAUNCH_OK("k_pcg_direction");
-            prof_mark(st, 2, used);
-            w.S.par ^= 1;
+    auto iteration = [&]() -> int {
+        k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
+        DFDM_LAUNCH_OK("k_pcg_spmv");
+        prof_mark(st, 0, used);
+        k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
+                                                                                mg ? 1 : 0);
+        DFDM_LAUNCH_OK("k_pcg_update");
+        prof_mark(st, 1, used);
+        if (mg) {
+            int rc = mg_vcycle(P, *M, base, B, w, 0, st, used, mp, over_w, w_levels);
+            if (rc) return rc;
+            prof_mark(st, -1, used);
         }
-        DFDM_CUDA_OK(cudaMemcpyAsync(host_flag, w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        DFDM_CUDA_OK(cudaStreamSynchronize(st));
-        prof_resolve(used);
-        if (*host_flag == 0) break;
+        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r,
+                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1);
+        DFDM_LAUNCH_OK("k_pcg_direction");
+        prof_mark(st, 2, used);
+        w.S.par ^= 1;
+        return DFDM_OK;
+    };
+    int it = 0;
+    if (every > 0) {
+        // blocking polls: the host waits for the device every `every` iterations
+        while (it < maxiter) {
+            int stop = std::min(maxiter, it + every);
+            used = 0;
+            prof_mark(st, -1, used);
+            for (; it < stop; ++it) {
+                int rc = iteration();
+                if (rc) return rc;
+            }
+            DFDM_CUDA_OK(cudaMemcpyAsync(host_flag, w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            DFDM_CUDA_OK(cudaStreamSynchronize(st));
+            prof_resolve(used);
+            if (*host_flag == 0) break;
+        }
+        *iters_out = it;
+        return DFDM_OK;
     }
-    *iters_out = it;
+    // look-ahead polls: the counter of every iteration is copied to pinned memory behind it; the host enqueues
+    // iteration k only after iteration k - kAhead has completed and shown unconverged columns.  The device always has
+    // work queued, nothing is rounded up to a polling interval, and the kAhead iterations enqueued past convergence
+    // exit at their first instruction (every kernel tests the counter snapshot of the previous iteration).
+    constexpr int kAhead = 2, kSlots = 4;
+    static thread_local cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < kSlots; ++k)
+        if (!done[k]) DFDM_CUDA_OK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    int32_t* flags = host_flag + 1;                                    // host_flag[0] is the verdict the caller reads
+    used = 0;
+    prof_mark(st, -1, used);
+    int converged_at = -1, checked = 0;
+    auto check = [&](int k) -> int {                                   // has iteration k (0-based) left nothing active?
+        DFDM_CUDA_OK(cudaEventSynchronize(done[k % kSlots]));
+        if (flags[k % kSlots] == 0 && converged_at < 0) converged_at = k + 1;
+        return DFDM_OK;
+    };
+    while (it < maxiter && converged_at < 0) {
+        if (it >= kAhead) {
+            int rc = check(checked++);
+            if (rc) return rc;
+            if (converged_at >= 0) break;
+        }
+        int rc = iteration();
+        if (rc) return rc;
+        DFDM_CUDA_OK(cudaMemcpyAsync(&flags[it % kSlots], w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        DFDM_CUDA_OK(cudaEventRecord(done[it % kSlots], st));
+        prof_mark(st, -1, used);                                       // the 4-byte copy is not part of the next kernel's interval
+        ++it;
+    }
+    for (; checked < it && converged_at < 0; ++checked) {
+        int rc = check(checked);
+        if (rc) return rc;
+    }
+    DFDM_CUDA_OK(cudaStreamSynchronize(st));
+    prof_resolve(used);
+    *host_flag = converged_at >= 0 ? 0 : 1;
+    *iters_out = converged_at >= 0 ? converged_at : it;
     return DFDM_OK;
 }
 

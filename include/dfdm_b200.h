@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DFDM_ABI_VERSION 1
+#define DFDM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DFDM_API __attribute__((visibility("default")))
@@ -61,12 +61,20 @@ typedef struct dfdm_options {
     int32_t solver;          /* DFDM_SOLVER_*; AUTO picks DIRECT when the band fits shared memory */
     int32_t pcg_maxiter;     /* <= 0: default 20 * sqrt(n_free) + 2000 */
     double pcg_rtol;         /* <= 0: default 1e-12 on ||r|| / ||b|| per design and coordinate */
-    int32_t pcg_check_every; /* host polls the device "all converged" flag every k iterations; <= 0: 25 (Jacobi) / 5 (multigrid) */
+    int32_t pcg_check_every; /* > 0: the host blocks on the device "all converged" counter every k iterations;
+                                <= 0 (default): the host stays two iterations ahead of the device and reads the counter of
+                                every iteration as it completes, so the device never waits for the host and at most two
+                                (early-exiting, empty) iterations are enqueued past convergence */
     int32_t pcg_precond;     /* DFDM_PRECOND_*; AUTO = aggregation multigrid V-cycle when the plan has coarse levels */
     double mg_omega;         /* damping of the Jacobi smoother; <= 0: default 0.8 */
-    double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects); <= 0: 1.5 (W) / 1.7 (V) */
+    double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects) on levels whose coarse
+                                problem is solved once or exactly; the scalings of such nested levels multiply.
+                                <= 0: 1.3 under a W-cycle, 1.7 for a plain V-cycle */
     int32_t mg_w_levels;     /* coarse levels 1..k are visited twice per cycle (W-cycle); 0: default 2; < 0: plain V-cycle */
     int32_t reserved;
+    double mg_over_w;        /* the same scaling on levels whose coarse problem is solved TWICE (the finest level and the W
+                                levels but the last): two nested corrections of scaling s combine to 1 - (1 - s)^2 <= 1, so any
+                                value below 2 keeps the preconditioner definite.  <= 0: 1.7 */
 } dfdm_options;
 
 /* preconditioner of the PCG path */
