@@ -200,6 +200,34 @@ __global__ void __launch_bounds__(kThreads) k_assemble(PlanDev P, LaneCfg cfg, i
 
 constexpr int kVecThreads = 384;
 
+// Programmatic dependent launch: the kernels of one PCG iteration form a chain on one stream, each a full wave of
+// the GPU.  Launched with the "programmatic stream serialization" attribute, kernel k+1 is set up and its CTAs are
+// placed while kernel k drains; it then waits here, at its first instruction, until kernel k has completed and its
+// writes are visible.  That takes the launch latency out of the ~25 kernel boundaries of an iteration.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (an early griddepcontrol.launch_dependents after the wait was measured: 1 % slower - the waiting CTAs of the next
+// kernel take issue slots from the tail of this one)
+
+static bool pdl_enabled() {
+    static const bool on = !(std::getenv("DFDM_PDL") && std::atoi(std::getenv("DFDM_PDL")) == 0);
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 #define VEC_SETUP()                                                         \
     const int cbl = 1 << cfg.shift;                                         \
     const int chunk = blockIdx.x % cfg.nchunks;                             \
@@ -309,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
                                                                           const double* __restrict__ vals,
                                                                           const double* __restrict__ p, double* __restrict__ Ap,
                                                                           PcgScalars S) {
+    pdl_wait();
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     LANE_SETUP();
     double v[3] = {0, 0, 0};
@@ -374,6 +403,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
                                                                               const double* __restrict__ dinv,
                                                                               const double* __restrict__ Ap, double* __restrict__ r,
                                                                               PcgScalars S, double tol2, int mg) {
+    pdl_wait();
     // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     VEC_SETUP();
@@ -421,6 +451,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
 __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                               const double* __restrict__ r, const float* __restrict__ z,
                                                               double* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd) {
+    pdl_wait();
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1 + (S.par ^ 1)] = __ldcg(&S.n_active[0]);
     VEC_SETUP();
@@ -583,6 +614,7 @@ template <typename TB, int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, LaneCfg cfg, int B, const TB* __restrict__ bvec,
                                                         mgf* __restrict__ t, mgf* __restrict__ b_coarse,
                                                         const int32_t* __restrict__ n_active, MgParams mp) {
+    pdl_wait();
     if (__ldcg(&n_active[1]) == 0) return;
     LANE_SETUP_V();
     if (!live) return;
@@ -623,6 +655,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
                                                       const mgf* __restrict__ t, const mgf* __restrict__ e_coarse,
                                                       mgf* __restrict__ z, PcgScalars S, int dots, int first, MgParams mp) {
     // ACC: the W-cycle's second visit adds its correction to the first one (already in z) instead of in a separate pass
+    pdl_wait();
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
     LANE_SETUP_V();
     double dsum[3][V];
@@ -783,6 +816,7 @@ __device__ __forceinline__ Vf<2> ldcg2(const float* p) {
 template <int LANES>
 __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, int B, const mgf* rhs, mgf* out, int acc,
                                                               const int32_t* __restrict__ n_active, MgParams mp) {
+    pdl_wait();
     if (__ldcg(&n_active[1]) == 0) return;                 // uniform over the grid: no CTA is left waiting at a barrier
     constexpr int V = 2;
     constexpr int U = kBottomU;
@@ -1020,6 +1054,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, int B, const mgf* __restrict__ rhs,
                                                          const mgf* __restrict__ x, mgf* __restrict__ r2,
                                                          const int32_t* __restrict__ n_active) {
+    pdl_wait();
     if (__ldcg(&n_active[1]) == 0) return;
     LANE_SETUP_V();
     if (!live) return;
@@ -1085,6 +1120,7 @@ __global__ void __launch_bounds__(256) k_mg_coarsest_invert(int n, const int32_t
 // designs are staged in shared memory once, every thread then streams one row of the (symmetric) inverse.
 __global__ void __launch_bounds__(256) k_mg_coarsest_solve(int n, int B, const mgf* __restrict__ inv, const mgf* __restrict__ bvec,
                                                           mgf* __restrict__ e, const int32_t* __restrict__ n_active) {
+    pdl_wait();
     if (__ldcg(&n_active[1]) == 0) return;
     extern __shared__ float sb[];                          // [n][3][32]
     const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -1118,6 +1154,7 @@ __global__ void __launch_bounds__(256) k_mg_coarsest_solve(int n, int B, const m
 // coarsest level too large for a dense factor: a fixed number of damped Jacobi sweeps from a zero guess
 __global__ void k_mg_coarsest_jacobi(MgMat A, int B, int sweeps, const mgf* __restrict__ bvec, mgf* __restrict__ e,
                                      mgf* __restrict__ tmp, const int32_t* __restrict__ n_active, MgParams mp) {
+    pdl_wait();
     if (__ldcg(&n_active[1]) == 0) return;
     // one CTA per design (all rows, three coordinates): rows in a loop, sweeps separated by block barriers
     int b = blockIdx.x;
@@ -1670,19 +1707,19 @@ static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out, const
     MgMat A = mg_mat(*c.P, M, w, l);
     const MgParams mp = l < c.w_levels ? c.mp : c.mp_single;
     LaneCfg cd = rows_cfg(k_mg_down<mgf, V>, c.vbase, M.lv[l].n);
-    k_mg_down<mgf, V><<<cd.nchunks * cd.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cd, c.B, rhs, w.mg.t[l], w.mg.b[l + 1],
-                                                                      w.S.n_active + w.S.par, mp);
+    DFDM_CUDA_OK(launch_chain(k_mg_down<mgf, V>, cd.nchunks * cd.nslabs, kThreads, 0, c.st, A, M.lv[l], cd, c.B, rhs, w.mg.t[l], w.mg.b[l + 1],
+                                                                      w.S.n_active + w.S.par, mp));
     DFDM_LAUNCH_OK("k_mg_down");
     int rc = mg_solve_level<V>(c, l + 1, w.mg.b[l + 1], w.mg.z[l + 1]);
     if (rc) return rc;
     if (acc) {
         LaneCfg cu = rows_cfg(k_mg_up<mgf, V, true>, c.vbase, A.n);
-        k_mg_up<mgf, V, true><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
-                                                                              0, 0, mp);
+        DFDM_CUDA_OK(launch_chain(k_mg_up<mgf, V, true>, cu.nchunks * cu.nslabs, kThreads, 0, c.st, A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
+                                                                              0, 0, mp));
     } else {
         LaneCfg cu = rows_cfg(k_mg_up<mgf, V, false>, c.vbase, A.n);
-        k_mg_up<mgf, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, c.st>>>(A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
-                                                                               0, 0, mp);
+        DFDM_CUDA_OK(launch_chain(k_mg_up<mgf, V, false>, cu.nchunks * cu.nslabs, kThreads, 0, c.st, A, M.lv[l], cu, c.B, rhs, w.mg.t[l], w.mg.z[l + 1], out, w.S,
+                                                                               0, 0, mp));
     }
     DFDM_LAUNCH_OK("k_mg_up");
     return DFDM_OK;
@@ -1746,13 +1783,15 @@ static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
     cfg.blockDim = dim3(kBottomThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c.st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kBottomCluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, c.B, rhs, out, acc, (const int32_t*)(w.S.n_active + w.S.par), c.mp_single));
     DFDM_LAUNCH_OK("k_mg_bottom");
     return DFDM_OK;
@@ -1769,11 +1808,11 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
         if (w.mg.inv) {
             dim3 grid((unsigned)((c.B + 31) / 32), (unsigned)((C.n + 7) / 8));
             size_t smem = sizeof(float) * (size_t)C.n * 3 * 32;
-            k_mg_coarsest_solve<<<grid, 256, smem, c.st>>>(C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par);
+            DFDM_CUDA_OK(launch_chain(k_mg_coarsest_solve, grid, 256, smem, c.st, C.n, c.B, w.mg.inv, rhs, out, w.S.n_active + w.S.par));
             DFDM_LAUNCH_OK("k_mg_coarsest_solve");
         } else {
             MgMat A = mg_mat(*c.P, M, w, nl);
-            k_mg_coarsest_jacobi<<<c.B, 256, 0, c.st>>>(A, c.B, 24, rhs, out, w.mg.tmp, w.S.n_active + w.S.par, c.mp);
+            DFDM_CUDA_OK(launch_chain(k_mg_coarsest_jacobi, c.B, 256, 0, c.st, A, c.B, 24, rhs, out, w.mg.tmp, w.S.n_active + w.S.par, c.mp));
             DFDM_LAUNCH_OK("k_mg_coarsest_jacobi");
         }
         return DFDM_OK;
@@ -1784,7 +1823,7 @@ static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
         // second visit on the residual of the first: out += M_l (rhs - A_l out)
         MgMat A = mg_mat(*c.P, M, w, l);
         LaneCfg cr = rows_cfg(k_mg_resid<V>, c.vbase, A.n);
-        k_mg_resid<V><<<cr.nchunks * cr.nslabs, kThreads, 0, c.st>>>(A, cr, c.B, rhs, out, w.mg.r2[l], w.S.n_active + w.S.par);
+        DFDM_CUDA_OK(launch_chain(k_mg_resid<V>, cr.nchunks * cr.nslabs, kThreads, 0, c.st, A, cr, c.B, rhs, out, w.mg.r2[l], w.S.n_active + w.S.par));
         DFDM_LAUNCH_OK("k_mg_resid");
         rc = mg_cycle_level<V>(c, l, w.mg.r2[l], out, out);
         if (rc) return rc;
@@ -1809,8 +1848,8 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     MgMat A = mg_mat(P, M, w, 0);
     LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
-    k_mg_down<double, V><<<cd.nchunks * cd.nslabs, kThreads, 0, st>>>(A, M.lv[0], cd, B, w.r, w.mg.t[0], w.mg.b[1],
-                                                                     w.S.n_active + w.S.par, mp);
+    DFDM_CUDA_OK(launch_chain(k_mg_down<double, V>, cd.nchunks * cd.nslabs, kThreads, 0, st, A, M.lv[0], cd, B, w.r, w.mg.t[0], w.mg.b[1],
+                                                                     w.S.n_active + w.S.par, mp));
     DFDM_LAUNCH_OK("k_mg_down");
     prof_mark(st, 3, used);
     int rc = mg_solve_level<V>(c, 1, w.mg.b[1], w.mg.z[1]);
@@ -1818,8 +1857,8 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     prof_mark(st, 5, used);                              // everything below the finest level, per cycle
     LaneCfg cu = rows_cfg(k_mg_up<double, V, false>, c.vbase, A.n, up_tiles);
     const MgParams mp0 = w_levels > 0 ? mpw : mp;     // level 1 is solved twice whenever there is a W level
-    k_mg_up<double, V, false><<<cu.nchunks * cu.nslabs, kThreads, 0, st>>>(A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0],
-                                                                          w.S, 1, first, mp0);
+    DFDM_CUDA_OK(launch_chain(k_mg_up<double, V, false>, cu.nchunks * cu.nslabs, kThreads, 0, st, A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0],
+                                                                          w.S, 1, first, mp0));
     DFDM_LAUNCH_OK("k_mg_up");
     prof_mark(st, 4, used);
     return DFDM_OK;
@@ -1885,17 +1924,17 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     if (mg) {
         int rc = mg_vcycle(P, *M, base, B, w, 1, st, used, mp, over_w, w_levels);   // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
-        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
-                                                                                   w.S, 0);
+        DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
+                                                                                   w.S, 0));
         DFDM_LAUNCH_OK("k_pcg_direction");
         w.S.par ^= 1;
     }
     auto iteration = [&]() -> int {
-        k_pcg_spmv<<<cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st>>>(P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S);
+        DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S));
         DFDM_LAUNCH_OK("k_pcg_spmv");
         prof_mark(st, 0, used);
-        k_pcg_update<<<cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
-                                                                                mg ? 1 : 0);
+        DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
+                                                                                mg ? 1 : 0));
         DFDM_LAUNCH_OK("k_pcg_update");
         prof_mark(st, 1, used);
         if (mg) {
@@ -1903,8 +1942,8 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             if (rc) return rc;
             prof_mark(st, -1, used);
         }
-        k_pcg_direction<<<cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st>>>(P.nf, cfg_dir, B, w.dinv, w.r,
-                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1);
+        DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r,
+                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1));
         DFDM_LAUNCH_OK("k_pcg_direction");
         prof_mark(st, 2, used);
         w.S.par ^= 1;
@@ -1941,6 +1980,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     used = 0;
     prof_mark(st, -1, used);
     int converged_at = -1, checked = 0;
+    std::vector<size_t> mark_at;                                       // profiling: first event of every iteration
     auto check = [&](int k) -> int {                                   // has iteration k (0-based) left nothing active?
         DFDM_CUDA_OK(cudaEventSynchronize(done[k % kSlots]));
         if (flags[k % kSlots] == 0 && converged_at < 0) converged_at = k + 1;
@@ -1952,6 +1992,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             if (rc) return rc;
             if (converged_at >= 0) break;
         }
+        mark_at.push_back(used);
         int rc = iteration();
         if (rc) return rc;
         DFDM_CUDA_OK(cudaMemcpyAsync(&flags[it % kSlots], w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1964,7 +2005,8 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
         if (rc) return rc;
     }
     DFDM_CUDA_OK(cudaStreamSynchronize(st));
-    prof_resolve(used);
+    // the iterations enqueued past convergence are empty launches: they must not dilute the per-kernel averages
+    prof_resolve(converged_at >= 0 && converged_at < it ? mark_at[converged_at] : used);
     *host_flag = converged_at >= 0 ? 0 : 1;
     *iters_out = converged_at >= 0 ? converged_at : it;
     return DFDM_OK;
