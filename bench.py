@@ -331,7 +331,7 @@ def gpu_arm(args, rank, world, local_rank):
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
-                       "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 2))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
+                       "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients)" % world,
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
                        "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
@@ -422,7 +422,7 @@ def coarse_cycle_bytes(plan, mg_w_levels):
     nnzs = [int(v) for v in plan.array(_lib.ARR_MG_NNZ)]
     if len(rows) < 2:
         return 0.0
-    w = 0 if mg_w_levels < 0 else (mg_w_levels or 2)
+    w = 0 if mg_w_levels < 0 else (mg_w_levels or 3)
     last = len(rows) - 1
     total, visits = 0.0, 1
     for l in range(1, last + 1):
@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--mg-omega", type=float, default=0.0)
     ap.add_argument("--mg-over", type=float, default=0.0)
     ap.add_argument("--mg-over-w", type=float, default=0.0)
-    ap.add_argument("--mg-w-levels", type=int, default=0, help="coarse levels visited twice per cycle (0: default 2, -1: V-cycle)")
+    ap.add_argument("--mg-w-levels", type=int, default=0, help="coarse levels visited twice per cycle (0: default 3, -1: V-cycle)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the second, event-instrumented timed region (no per-kernel table)")

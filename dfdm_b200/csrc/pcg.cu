@@ -1899,8 +1899,9 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
                           cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap) {
     const bool mg = M != nullptr && M->n_levels > 0;
     // cycle shape: coarse levels 1 .. w_levels are visited twice (W-cycle); deeper levels once.  Plain aggregation gains
-    // most from revisiting the first coarse levels, and the tiny ones below are latency bound, so the default is 2.
-    int w_levels = opt.mg_w_levels < 0 ? 0 : (opt.mg_w_levels > 0 ? opt.mg_w_levels : 2);
+    // most from revisiting the first coarse levels; the tiny ones below are latency bound (8 visits of the cluster kernel
+    // per cycle is where a fourth W level stops paying), so the default is 3.
+    int w_levels = opt.mg_w_levels < 0 ? 0 : (opt.mg_w_levels > 0 ? opt.mg_w_levels : 3);
     if (mg) w_levels = std::min(w_levels, std::max(0, M->n_levels - 1));
     MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault),
                 (float)(opt.mg_over > 0 ? opt.mg_over : (w_levels > 0 ? kMgOverW : kMgOverDefault))};

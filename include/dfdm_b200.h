@@ -70,7 +70,7 @@ typedef struct dfdm_options {
     double mg_over;          /* scaling of the coarse-grid correction (plain aggregation under-corrects) on levels whose coarse
                                 problem is solved once or exactly; the scalings of such nested levels multiply.
                                 <= 0: 1.3 under a W-cycle, 1.7 for a plain V-cycle */
-    int32_t mg_w_levels;     /* coarse levels 1..k are visited twice per cycle (W-cycle); 0: default 2; < 0: plain V-cycle */
+    int32_t mg_w_levels;     /* coarse levels 1..k are visited twice per cycle (W-cycle); 0: default 3; < 0: plain V-cycle */
     int32_t reserved;
     double mg_over_w;        /* the same scaling on levels whose coarse problem is solved TWICE (the finest level and the W
                                 levels but the last): two nested corrections of scaling s combine to 1 - (1 - s)^2 <= 1, so any
