@@ -96,8 +96,17 @@ __device__ bool publish_partials(double (&v)[NV], const LaneCfg& cfg, int B, dou
 
 template <int NV>
 __device__ __forceinline__ double sum_slabs(const double* partial, int c, int b, int B, int nslabs) {
+    // one thread sums ~90 partials in slab order (fixed order: bit-reproducible).  The loads are issued 8 at a time;
+    // one by one they are a chain of ~90 L2 round trips at the tail of every kernel that reduces.
+    constexpr int U = 8;
     double s = 0.0;
-    for (int sl = 0; sl < nslabs; ++sl) s += __ldcg(&partial[((size_t)sl * NV + c) * B + b]);
+    for (int s0 = 0; s0 < nslabs; s0 += U) {
+        double t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = s0 + u < nslabs ? __ldcg(&partial[((size_t)(s0 + u) * NV + c) * B + b]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += t[u];
+    }
     return s;
 }
 
@@ -1974,7 +1983,11 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     // work queued, nothing is rounded up to a polling interval, and the kAhead iterations enqueued past convergence
     // exit at their first instruction (every kernel tests the counter snapshot of the previous iteration).
     constexpr int kAhead = 2, kSlots = 4;
-    static thread_local cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    struct Events { cudaEvent_t e[kSlots] = {nullptr, nullptr, nullptr, nullptr}; };
+    static thread_local std::map<int, Events> per_device;              // events belong to the device they were created on
+    int dev = 0;
+    DFDM_CUDA_OK(cudaGetDevice(&dev));
+    cudaEvent_t* done = per_device[dev].e;
     for (int k = 0; k < kSlots; ++k)
         if (!done[k]) DFDM_CUDA_OK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
     int32_t* flags = host_flag + 1;                                    // host_flag[0] is the verdict the caller reads
