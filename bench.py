@@ -230,7 +230,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w)
+                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w, flags=(_lib.FLAG_SPMV_MATRIX_FREE if args.spmv_matrix_free else 0))
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -343,7 +343,7 @@ def gpu_arm(args, rank, world, local_rank):
         nc = plan.info.get("mg_n_coarse", 0)
         is_mg = plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi"
         # update: r in/out, Ap (+ 1/diag for Jacobi); direction: p in/out, x in/out, z (float) or r + 1/diag
-        alg = {"k_pcg_spmv": (8.0 * nnz + 48.0 * nf) * batch, "k_pcg_update": (72.0 if is_mg else 80.0) * nf * batch,
+        alg = {"k_pcg_spmv": ((8.0 * E if args.spmv_matrix_free else 8.0 * nnz) + 48.0 * nf) * batch, "k_pcg_update": (72.0 if is_mg else 80.0) * nf * batch,
                "k_pcg_direction": (108.0 if is_mg else 128.0) * nf * batch,
                # single-precision V-cycle: K D^-1 (4 nnz), r in double (24 nf), t out (12 nf), coarse rhs out (12 nc)
                "k_mg_down[level 0]": (4.0 * nnz + 36.0 * nf + 12.0 * nc) * batch,
@@ -472,6 +472,7 @@ def main():
     ap.add_argument("--mg-omega", type=float, default=0.0)
     ap.add_argument("--mg-over", type=float, default=0.0)
     ap.add_argument("--mg-over-w", type=float, default=0.0)
+    ap.add_argument("--spmv-matrix-free", action="store_true", help="K p from q over the incidence lists instead of the stored CSR values")
     ap.add_argument("--mg-w-levels", type=int, default=0, help="coarse levels visited twice per cycle (0: default 3, -1: V-cycle)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")

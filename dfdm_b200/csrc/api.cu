@@ -25,7 +25,7 @@ static int upload_plan(const Plan& P, int device, PlanDev& out, PlanDev& out_pcg
                                             &P.finc_ptr, &P.finc_edge, &P.finc_code, &P.ninc_ptr, &P.ninc_edge, &P.ninc_sign,
                                             &P.perm, &P.pos, &P.sinc_ptr, &P.sinc_edge, &P.sinc_code, &P.ell_col,
                                             &P.pg.free_nodes, &P.pg.node_src, &P.pg.rowptr, &P.pg.colidx, &P.pg.diagslot, &P.pg.ell_col,
-                                            &P.pg.finc_ptr, &P.pg.finc_edge, &P.pg.finc_code};
+                                            &P.pg.finc_ptr, &P.pg.finc_edge, &P.pg.finc_code, &P.pg.inc_edge, &P.pg.inc_col};
     constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
     int64_t offs[NA], total = 0;
     for (int k = 0; k < NA; ++k) {
@@ -48,6 +48,7 @@ static int upload_plan(const Plan& P, int device, PlanDev& out, PlanDev& out_pcg
     PlanDev g = d;                                    // the PCG path's view: same network, rows in its own order
     g.free_nodes = at(18); g.node_src = at(19); g.rowptr = at(20); g.colidx = at(21); g.diagslot = at(22);
     g.ell_w = P.pg.ell_w; g.ell_col = at(23); g.finc_ptr = at(24); g.finc_edge = at(25); g.finc_code = at(26);
+    g.inc_w = P.pg.inc_w; g.inc_edge = at(27); g.inc_col = at(28);
     g.perm = nullptr; g.pos = nullptr; g.sinc_ptr = nullptr; g.sinc_edge = nullptr; g.sinc_code = nullptr;
     P.dev_pcg[device] = g;
     P.dev_block[device] = block;

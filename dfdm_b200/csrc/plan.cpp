@@ -320,6 +320,17 @@ static void build_rowset(const Plan& P, const std::vector<int32_t>& free_nodes, 
             R.finc_edge[k] = seg[t].second;
         }
     }
+    // padded incidence for the matrix-free product (K p)_f = sum_e q_e (p_f - p_other(e))
+    R.inc_w = 0;
+    for (int f = 0; f < nf; ++f) R.inc_w = std::max(R.inc_w, R.finc_ptr[f + 1] - R.finc_ptr[f]);
+    if (R.inc_w > 16) R.inc_w = 0;                       // hubs: keep the stored matrix
+    R.inc_edge.assign((size_t)nf * R.inc_w, -1);
+    R.inc_col.assign((size_t)nf * R.inc_w, -1);
+    for (int f = 0; f < nf && R.inc_w > 0; ++f)
+        for (int k = R.finc_ptr[f], u = 0; k < R.finc_ptr[f + 1]; ++k, ++u) {
+            R.inc_edge[(size_t)f * R.inc_w + u] = R.finc_edge[k];
+            R.inc_col[(size_t)f * R.inc_w + u] = R.finc_code[k] >= 0 ? R.colidx[R.finc_code[k]] : -1;
+        }
 }
 
 // The PCG path numbers its rows hierarchically: rows of one aggregate are contiguous, aggregates of one

@@ -30,6 +30,11 @@ struct PlanDev {
     const int32_t* finc_ptr = nullptr;    // [nf+1]
     const int32_t* finc_edge = nullptr;
     const int32_t* finc_code = nullptr;
+    // the same incidence padded to inc_w entries per row (PCG row set only; inc_w = 0 when a node has too many edges):
+    // edge (-1 for padding) and the free row of its other end (-1: fixed).  K p straight from q: no stored matrix.
+    int inc_w = 0;
+    const int32_t* inc_edge = nullptr;    // [nf][inc_w]
+    const int32_t* inc_col = nullptr;     // [nf][inc_w]
     // node incidence (all nodes): C[e, node]
     const int32_t* ninc_ptr = nullptr;    // [n+1]
     const int32_t* ninc_edge = nullptr;
@@ -77,6 +82,8 @@ struct RowSet {
     std::vector<int32_t> node_src;       // [n]  row of a free node, or -1 - k for fixed node k
     std::vector<int32_t> rowptr, colidx, diagslot, ell_col;
     std::vector<int32_t> finc_ptr, finc_edge, finc_code;
+    int inc_w = 0;
+    std::vector<int32_t> inc_edge, inc_col;
 };
 
 struct Plan {

@@ -71,11 +71,15 @@ typedef struct dfdm_options {
                                 problem is solved once or exactly; the scalings of such nested levels multiply.
                                 <= 0: 1.3 under a W-cycle, 1.7 for a plain V-cycle */
     int32_t mg_w_levels;     /* coarse levels 1..k are visited twice per cycle (W-cycle); 0: default 3; < 0: plain V-cycle */
-    int32_t reserved;
+    int32_t flags;           /* DFDM_FLAG_* bits; 0: defaults */
     double mg_over_w;        /* the same scaling on levels whose coarse problem is solved TWICE (the finest level and the W
                                 levels but the last): two nested corrections of scaling s combine to 1 - (1 - s)^2 <= 1, so any
                                 value below 2 keeps the preconditioner definite.  <= 0: 1.7 */
 } dfdm_options;
+
+/* option flags */
+#define DFDM_FLAG_SPMV_MATRIX_FREE 1   /* PCG: K p straight from q over the node-edge incidence (8 E bytes per design) instead of
+                                          the stored CSR values (8 nnz): 7 % faster SpMV on the quad grid, 0.8 % per evaluation */
 
 /* preconditioner of the PCG path */
 #define DFDM_PRECOND_AUTO 0

@@ -378,3 +378,38 @@ def test_multigrid_pcg_on_an_irregular_triangulation():
         assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
     f, a = _lib.last_pcg_iterations()
     assert f <= 80 and a <= 80, (f, a)                                             # multigrid, not the Jacobi fallback
+
+
+@pytest.mark.parametrize("mesh", ["grid", "delaunay"])
+def test_matrix_free_spmv_gives_the_same_answers(mesh):
+    """DFDM_FLAG_SPMV_MATRIX_FREE: K p from q over the incidence lists (fixed neighbours, ragged degrees) vs the stored CSR values."""
+    from dfdm_b200 import workloads as W
+    if mesh == "grid":
+        edges, fixed, xyz, loads, q0 = W.grid_arrays(40)
+        q = W.sample_q(q0, 6, seed=3, spread=0.5, relative=True)
+    else:
+        from scipy.spatial import Delaunay
+        rng = np.random.default_rng(5)
+        pts = rng.random((3000, 2))
+        tri = Delaunay(pts)
+        pairs = np.vstack([tri.simplices[:, [0, 1]], tri.simplices[:, [1, 2]], tri.simplices[:, [2, 0]]])
+        edges = np.unique(np.sort(pairs, axis=1), axis=0).astype(np.int32)
+        fixed = np.zeros(len(pts), dtype=np.uint8)
+        fixed[np.unique(tri.convex_hull)] = 1
+        xyz = np.column_stack([pts, 0.1 * np.cos(4.0 * pts[:, 0])])
+        loads = np.zeros_like(xyz)
+        loads[:, 2] = -1.0 / len(pts)
+        q = 1.0 + 0.6 * (rng.random((6, len(edges))) - 0.5)
+    plan = Plan(len(fixed), edges, fixed)
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    outs = []
+    for flags in (0, _lib.FLAG_SPMV_MATRIX_FREE):
+        ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", flags=flags)
+        out = ev.loss_and_grad(prog, q, outputs=("xyz",))
+        assert np.all(out["status"].cpu().numpy() == 0)
+        outs.append({k: out[k].cpu().numpy() for k in ("xyz", "loss", "dq")})
+    assert _rel(outs[1]["xyz"], outs[0]["xyz"]) < TOL_X
+    assert _rel(outs[1]["loss"], outs[0]["loss"]) < 1e-9
+    assert _rel(outs[1]["dq"], outs[0]["dq"]) < TOL_G
