@@ -61,3 +61,11 @@ def test_ensemble_and_cable_net():
     assert np.all(value_opt <= value)
     loss = _load("cable_net").main(nfree=64, batch=8, verbose=False)
     assert np.all(np.isfinite(loss)) and loss.shape == (8,)
+
+
+def test_sharded_ensemble_on_one_rank():
+    """examples/ensemble_sharded.py with a world of one: the shard is the whole ensemble, the gathers are identities."""
+    start, end, q_opt = _load("ensemble_sharded").main(batch_per_gpu=128, maxiter=8, verbose=False)
+    assert start.shape == end.shape == (128,) and q_opt.shape[0] == 128
+    assert np.all(end <= start) and end.mean() < 0.7 * start.mean()
+    assert np.all(q_opt <= -1e-3 + 1e-12)
