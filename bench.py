@@ -210,7 +210,7 @@ def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     from dfdm_b200 import _lib
     from dfdm_b200.engine import Plan, GoalProgram, Evaluator
-    from dfdm_b200.distributed import gather_designs
+    from dfdm_b200.distributed import gather_designs, PeerGather
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -238,11 +238,27 @@ def gpu_arm(args, rank, world, local_rank):
     if args.steps <= 0:
         args.steps = 3 if solver == "pcg" else 50
 
+    # the one exchange of a batched evaluation: losses and gradients of every design on every rank.  Peer stores over
+    # NVLink (one kernel per tensor + a one-element all-reduce as the fence) when the ranks can map each other's
+    # memory, NCCL all-gather otherwise (DFDM_PEER_GATHER=0 forces it).
+    peer = None
+    if world > 1 and os.environ.get("DFDM_PEER_GATHER", "1") != "0" and PeerGather.available(batch * world):
+        try:
+            peer = (PeerGather(batch * world, (), device=device), PeerGather(batch * world, (E,), device=device))
+        except Exception as exc:                                    # no peer access on this box: NCCL does the same job
+            print("bench.py: peer gather unavailable (%s); using NCCL all-gather" % exc, file=sys.stderr)
+            peer = None
+
     def step():
         out = ev.loss_and_grad(prog, q_dev)
-        if world > 1:                                               # the one collective of a batched evaluation
-            loss_all = gather_designs(out["loss"], batch * world)
-            dq_all = gather_designs(out["dq"], batch * world)
+        if world > 1:
+            if peer:
+                loss_all = peer[0].gather(out["loss"], sync=False)
+                dq_all = peer[1].gather(out["dq"], sync=False)
+                peer[1].fence()
+            else:
+                loss_all = gather_designs(out["loss"], batch * world)
+                dq_all = gather_designs(out["dq"], batch * world)
             return out, loss_all, dq_all
         return out, out["loss"], out["dq"]
 
@@ -332,7 +348,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
                        "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
-                       "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients)" % world,
+                       "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients%s)" % (world, ": peer stores over NVLink" if peer else (": NCCL" if world > 1 else "")),
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
                        "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
             "clocks": clocks,

@@ -35,7 +35,8 @@ TERM_KINDS = {"SquaredError": 0, "MeanSquaredError": 1, "PredictionError": 2}
 SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan_destroy", "dfdm_plan_get_info",
            "dfdm_plan_array", "dfdm_goalprog_create", "dfdm_goalprog_destroy", "dfdm_workspace_bytes", "dfdm_forward",
            "dfdm_loss_and_grad", "dfdm_vjp", "dfdm_forward_host", "dfdm_loss_and_grad_host", "dfdm_launch_count",
-           "dfdm_last_pcg_iterations", "dfdm_profile_enable", "dfdm_profile_read"]
+           "dfdm_last_pcg_iterations", "dfdm_profile_enable", "dfdm_profile_read", "dfdm_peer_alloc", "dfdm_peer_open",
+           "dfdm_peer_close", "dfdm_peer_free", "dfdm_peer_push"]
 
 
 class Options(C.Structure):
@@ -86,6 +87,11 @@ def _load():
     lib.dfdm_profile_enable.restype = None
     lib.dfdm_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]
     lib.dfdm_profile_read.restype = None
+    lib.dfdm_peer_alloc.argtypes = [i64, C.POINTER(vp), C.c_char_p]
+    lib.dfdm_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.dfdm_peer_close.argtypes = [vp]
+    lib.dfdm_peer_free.argtypes = [vp]
+    lib.dfdm_peer_push.argtypes = [vp, i64, i64, C.POINTER(vp), i32, vp]
     for name in SYMBOLS:
         getattr(lib, name)
     if lib.dfdm_abi_version() != 2:

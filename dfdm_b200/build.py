@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdfdm_b200.so")
-SOURCES = ["plan.cpp", "api.cu", "direct.cu", "pcg.cu"]
+SOURCES = ["plan.cpp", "api.cu", "direct.cu", "pcg.cu", "peer.cu"]
 HEADERS = [os.path.join(ROOT, "include", "dfdm_b200.h"), os.path.join(CSRC, "plan.hpp"), os.path.join(CSRC, "common.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static"]

@@ -8,10 +8,11 @@ The reference evaluates one design at a time in one process (src/dfdm/optimizati
 module is what lets an ensemble / parameter sweep use 8 x B200.  Works with the ``nccl`` backend on
 GPUs and with ``gloo`` on CPU tensors (tests).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard", "gather_designs", "ensemble_mean", "ShardedBatch"]
+__all__ = ["shard_bounds", "shard", "gather_designs", "ensemble_mean", "ShardedBatch", "PeerGather"]
 
 
 def shard_bounds(batch, world_size, rank):
@@ -92,3 +93,105 @@ class ShardedBatch:
         batch = q.shape[0]
         loss, dq = self.evaluate(self.local_slice(q))
         return ensemble_mean(loss, dq, batch, self.group)
+
+
+class _DeviceView:
+    """Raw device memory as something ``torch.as_tensor`` can wrap (CUDA array interface, no copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class PeerGather:
+    """
+    The all-gather of a sharded evaluation done with peer stores over NVLink instead of NCCL.
+
+    Every rank owns ``buffers`` device buffers of ``[batch, *row_shape]`` that all other ranks have mapped through
+    CUDA IPC.  ``gather(local)`` launches ONE kernel (``dfdm_peer_push``) that stores this rank's rows into the buffer
+    of every rank, the own one included, at the rank's row offset; a one-element all-reduce behind it orders the
+    readers: when it completes on a rank, every rank's stores have completed.  The buffers alternate, so a rank may
+    still be reading the result of one evaluation while the peers already store the next one.
+
+    Needs equal shards (``batch % world_size == 0``), one process per GPU on one node, and ``torch.distributed``
+    initialised.  ``PeerGather.available()`` says whether the peer path can be used; ``gather_designs`` is the NCCL /
+    gloo equivalent for every other case.
+    """
+
+    _TYPES = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}
+
+    @staticmethod
+    def available(batch=None, group=None):
+        world, _ = _world(group)
+        if world < 2 or not torch.cuda.is_available() or dist.get_backend(group) != "nccl":
+            return False
+        return batch is None or batch % world == 0
+
+    def __init__(self, batch, row_shape=(), dtype=torch.float64, device=None, group=None, buffers=2):
+        import ctypes as C
+        from dfdm_b200 import _lib
+        self._lib, self._C = _lib, C
+        self.group = group
+        self.world, self.rank = _world(group)
+        if not self.available(batch, group):
+            raise RuntimeError("PeerGather needs >= 2 ranks on the nccl backend and a batch divisible by the world size")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.shape = (int(batch),) + tuple(int(v) for v in row_shape)
+        self.dtype = dtype
+        self.rows_local = batch // self.world
+        self.row_bytes = int(np.prod(self.shape[1:], dtype=np.int64)) * torch.empty((), dtype=dtype).element_size()
+        if (self.rows_local * self.row_bytes) % 16 != 0:
+            raise RuntimeError("PeerGather: a shard must be a multiple of 16 bytes")
+        total = self.shape[0] * self.row_bytes
+        self._own, self._peers, self._views = [], [], []
+        with torch.cuda.device(self.device):
+            for _ in range(buffers):
+                ptr = C.c_void_p()
+                handle = C.create_string_buffer(64)
+                _lib.check(_lib.lib.dfdm_peer_alloc(total, C.byref(ptr), handle))
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle.raw, group=group)
+                bases = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        bases.append(ptr.value)
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(_lib.lib.dfdm_peer_open(h, C.byref(p)))
+                        bases.append(p.value)
+                self._own.append(ptr.value)
+                self._peers.append(bases)
+                self._views.append(torch.as_tensor(_DeviceView(ptr.value, self.shape, self._TYPES[dtype]), device=self.device))
+        self._turn = 0
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dist.barrier(group=group)
+
+    def gather(self, local, sync=True):
+        """Store ``local`` (this rank's ``[batch / world, ...]`` rows) into every rank's buffer; returns the own, full one."""
+        C = self._C
+        local = local.contiguous()
+        if tuple(local.shape) != (self.rows_local,) + self.shape[1:] or local.dtype != self.dtype:
+            raise ValueError("PeerGather.gather: expected %r of %s" % ((self.rows_local,) + self.shape[1:], self.dtype))
+        k = self._turn
+        self._turn = (k + 1) % len(self._own)
+        bases = (C.c_void_p * self.world)(*self._peers[k])
+        nbytes = self.rows_local * self.row_bytes
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._lib.check(self._lib.lib.dfdm_peer_push(C.c_void_p(local.data_ptr()), nbytes, self.rank * nbytes, bases, self.world, stream))
+        if sync:
+            self.fence()
+        return self._views[k]
+
+    def fence(self):
+        """Orders this rank's readers after every rank's stores (a one-element all-reduce on the current stream)."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        for bases, own in zip(self._peers, self._own):
+            for r, p in enumerate(bases):
+                if r != self.rank:
+                    self._lib.lib.dfdm_peer_close(self._C.c_void_p(p))
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for own in self._own:
+            self._lib.lib.dfdm_peer_free(self._C.c_void_p(own))
+        self._peers, self._own, self._views = [], [], []

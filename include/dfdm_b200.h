@@ -237,6 +237,25 @@ DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_
 DFDM_API void dfdm_profile_enable(int32_t on);
 DFDM_API void dfdm_profile_read(double* ms /* [8] */, int64_t* count /* [8] */);
 
+/*
+ * Peer-memory all-gather for the multi-GPU path (one process per GPU on one node).  The reference evaluates one design
+ * per call in one process (src/dfdm/optimization.py:89-97) and has nothing to bind here; these entry points serve
+ * dfdm_b200/distributed.py::PeerGather, the one exchange of a sharded batched evaluation (losses and gradients).
+ *
+ *   dfdm_peer_alloc   device buffer that other processes can map; `handle` receives 64 bytes to send to the peers
+ *   dfdm_peer_open    map a peer's buffer from its handle (CUDA IPC, peer access enabled on demand)
+ *   dfdm_peer_push    ONE kernel copies `bytes` from src into every dst_bases[d] + dst_offset_bytes (st.global to peer
+ *                     addresses over NVLink / NVSwitch; the own buffer may be one of the destinations).  Asynchronous on
+ *                     `stream`; the caller orders the readers (e.g. a barrier / tiny all-reduce after it).
+ *                     bytes % 8 == 0, src and dst_offset_bytes 16-byte aligned, at most 16 destinations.
+ */
+DFDM_API int32_t dfdm_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle /* [64] */);
+DFDM_API int32_t dfdm_peer_open(const uint8_t* handle /* [64] */, void** ptr);
+DFDM_API int32_t dfdm_peer_close(void* ptr);
+DFDM_API int32_t dfdm_peer_free(void* ptr);
+DFDM_API int32_t dfdm_peer_push(const void* src, int64_t bytes, int64_t dst_offset_bytes, void* const* dst_bases, int32_t n_dst,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif
