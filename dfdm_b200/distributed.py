@@ -74,10 +74,12 @@ class ShardedBatch:
     ``Evaluator.loss_and_grad``); the class owns only the partition and the collective.
     """
 
-    def __init__(self, evaluate, group=None):
+    def __init__(self, evaluate, group=None, peer=True):
         self.evaluate = evaluate
         self.group = group
         self.world_size, self.rank = _world(group)
+        self.peer = peer              # gather with peer stores over NVLink when the ranks can (PeerGather.available)
+        self._gathers = {}
 
     def local_slice(self, q):
         return shard(q, self.world_size, self.rank)
@@ -87,6 +89,19 @@ class ShardedBatch:
         loss, dq = self.evaluate(self.local_slice(q))
         if not gather:
             return loss, dq
+        if self.peer and torch.is_tensor(dq) and dq.is_cuda and PeerGather.available(batch, self.group):
+            key = (batch, tuple(dq.shape[1:]), dq.dtype)
+            if key not in self._gathers:
+                try:
+                    self._gathers[key] = (PeerGather(batch, (), loss.dtype, loss.device, self.group),
+                                          PeerGather(batch, dq.shape[1:], dq.dtype, dq.device, self.group))
+                except RuntimeError:                    # odd shard sizes, no peer access: every rank takes the NCCL path
+                    self._gathers[key] = None
+            if self._gathers[key] is not None:
+                g_loss, g_dq = self._gathers[key]
+                loss_all, dq_all = g_loss.gather(loss, sync=False), g_dq.gather(dq, sync=False)
+                g_dq.fence()
+                return loss_all, dq_all
         return gather_designs(loss, batch, self.group), gather_designs(dq, batch, self.group)
 
     def ensemble(self, q):
