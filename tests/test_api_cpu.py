@@ -222,6 +222,11 @@ def test_sharded_batch_gathers_in_design_order(tmp_path, batch):
         assert torch.allclose(out["mean_dq"], (2.0 * q).mean(dim=0))
 
 
+def test_peer_gather_is_not_offered_without_nccl_ranks():
+    from dfdm_b200.distributed import PeerGather
+    assert not PeerGather.available() and not PeerGather.available(batch=8)
+
+
 def test_shard_bounds_cover_the_batch_exactly():
     from dfdm_b200.distributed import shard_bounds
     for batch in (1, 7, 8, 4096):

@@ -206,3 +206,36 @@ def test_stacked_constraints_equal_the_individual_ones():
     assert _rel(values, want_v) < 1e-9 and _rel(jac, want_j) < 1e-7
     lb, ub = stacked.bounds(g["q"])
     assert lb.shape == want_v.shape and np.all(lb == 0.0) and np.all(ub == 1.0)
+
+
+def test_peer_push_kernel_on_one_device():
+    """dfdm_peer_alloc / _push / _free inside one process: the kernel that stores a rank's rows into every mapped buffer
+    (here two buffers of this process), odd double counts included (16-byte body + 8-byte tail)."""
+    import ctypes as C
+    import torch
+    from dfdm_b200 import _lib
+    from dfdm_b200.distributed import _DeviceView
+    dev = torch.device("cuda", 0)
+    n_total, offset = 4099, 1024                                       # doubles; the offset is 16-byte aligned
+    ptrs, views = [], []
+    for _ in range(2):
+        p, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(_lib.lib.dfdm_peer_alloc(n_total * 8, C.byref(p), handle))
+        assert any(handle.raw)                                         # an IPC handle was produced
+        ptrs.append(p.value)
+        views.append(torch.as_tensor(_DeviceView(p.value, (n_total,), "<f8"), device=dev))
+        views[-1].zero_()
+    for count in (3075, 2048, 1):
+        src = torch.arange(1, count + 1, dtype=torch.float64, device=dev)
+        bases = (C.c_void_p * 2)(*ptrs)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib.dfdm_peer_push(C.c_void_p(src.data_ptr()), count * 8, offset * 8, bases, 2, stream))
+        torch.cuda.synchronize()
+        for v in views:
+            assert torch.equal(v[offset:offset + count], src)
+            assert float(v[:offset].abs().sum()) == 0.0 and float(v[offset + 3075:].abs().sum()) == 0.0
+    with pytest.raises(_lib.DfdmError):
+        _lib.check(_lib.lib.dfdm_peer_push(C.c_void_p(src.data_ptr()), 8, 8, bases, 2, stream))   # misaligned destination
+    del views
+    for p in ptrs:
+        _lib.check(_lib.lib.dfdm_peer_free(C.c_void_p(p)))
