@@ -1321,7 +1321,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_state(PlanDev P, LaneCfg cfg,
 }
 
 // R = P - C^T diag(q) U; node goals -> loss partial and direct cotangents of X and R
-__global__ void __launch_bounds__(kThreads) k_node_state(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
+__global__ void __launch_bounds__(kThreads, 3) k_node_state(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
                                                         const double* __restrict__ qT, const double* __restrict__ loads,
                                                         const double* __restrict__ X, const double* __restrict__ U,
                                                         double* __restrict__ R, double* __restrict__ Xb, double* __restrict__ Rb,
@@ -1389,7 +1389,7 @@ __global__ void k_network_goals(GoalProgDev G, int B, int nslabs, const double* 
 }
 
 // edge goals + reverse steps 1-3: Ub (total cotangent of U), partial dq
-__global__ void __launch_bounds__(kThreads) k_edge_adjoint(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
+__global__ void __launch_bounds__(kThreads, 3) k_edge_adjoint(PlanDev P, GoalProgDev G, int has_prog, int seeds, LaneCfg cfg, int B,
                                                           const double* __restrict__ qT, const double* __restrict__ U,
                                                           const double* __restrict__ Lg, const double* __restrict__ F,
                                                           const double* __restrict__ Rb, const double* __restrict__ lpbar,
