@@ -54,6 +54,44 @@ __device__ double cta_sum(double v, double* red, int nt) {
 // with k in the low kshift bits of its index, so the hot loops carry no integer division.
 __device__ void band_solve(const double* __restrict__ D, double* __restrict__ rhs, int nf, int w, int LD, int nt, int kshift) {
     const int tid = threadIdx.x;
+    if (w == 1) {
+        // chains (bandwidth 1): a sweep is one dependent multiply-add per row.  Thread c walks right-hand side c on its
+        // own - no barrier per column - with the next row's operands loaded ahead of the dependent chain.
+        if (tid < 3) {
+            double* r = rhs + (size_t)tid * nf;
+            const double* l = D + LD;
+            double y = r[0];
+            double ln = nf > 1 ? l[1] : 0.0, rn = nf > 1 ? r[1] : 0.0;
+            for (int j = 1; j < nf; ++j) {
+                const double lj = ln, rj = rn;
+                if (j + 1 < nf) { ln = l[j + 1]; rn = r[j + 1]; }
+                y = rj - lj * y;
+                r[j] = y;
+            }
+        }
+        cta_sync(nt);
+        for (int i = tid; i < nf; i += nt) {
+            double d = D[i];
+            rhs[i] /= d;
+            rhs[nf + i] /= d;
+            rhs[2 * nf + i] /= d;
+        }
+        cta_sync(nt);
+        if (tid < 3) {
+            double* r = rhs + (size_t)tid * nf;
+            const double* l = D + LD;
+            double x = r[nf - 1];
+            double ln = nf > 1 ? l[nf - 1] : 0.0, rn = nf > 1 ? r[nf - 2] : 0.0;
+            for (int j = nf - 1; j > 0; --j) {
+                const double lj = ln, rj = rn;
+                if (j > 1) { ln = l[j - 1]; rn = r[j - 2]; }
+                x = rj - lj * x;
+                r[j - 1] = x;
+            }
+        }
+        cta_sync(nt);
+        return;
+    }
     const int span = 3 << kshift, kmask = (1 << kshift) - 1;
     for (int j = 0; j < nf - 1; ++j) {                       // forward: L y = b
         int m = min(w, nf - 1 - j);
@@ -130,7 +168,28 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
         cta_sync(nt);
 
         // ---- banded LDL^T, right-looking, in place ---------------------------------------------------
-        {
+        if (w == 1) {
+            // chains: d_(j+1) = K(j+1,j+1) - l^2 d_j with l = K(j+1,j) / d_j is one division and one multiply-add per row,
+            // strictly sequential; one thread runs it without the two barriers per column of the general path
+            if (tid == 0) {
+                const double* diag = D;
+                double* sub = D + LD;
+                double d = diag[0];
+                int bad = (d == 0.0 || !isfinite(d)) ? 1 : 0;
+                double en = nf > 1 ? sub[1] : 0.0, bn = nf > 1 ? diag[1] : 0.0;
+                for (int j = 0; j < nf - 1; ++j) {
+                    const double e = en, b2 = bn;
+                    if (j + 2 < nf) { en = sub[j + 2]; bn = diag[j + 2]; }
+                    const double l = e / d;
+                    d = b2 - l * e;
+                    sub[j + 1] = l;
+                    D[j + 1] = d;
+                    if (d == 0.0 || !isfinite(d)) bad = 1;
+                }
+                if (bad) s_bad = 1;
+            }
+            cta_sync(nt);
+        } else {
             const int TX = 1 << a.tx_shift, tx = tid & (TX - 1), ty = tid >> a.tx_shift, TY = nt >> a.tx_shift;
             for (int j = 0; j < nf - 1; ++j) {
                 int m = min(w, nf - 1 - j);
@@ -354,6 +413,7 @@ int run_direct(Eval& ev) {
 
     const int w = P.w;
     int nt = w <= 6 ? 32 : (w <= 12 ? 64 : (w <= 48 ? 128 : 256));
+    if (w == 1 && P.nf > 256) nt = 256;      // chains: the sweeps are single-threaded anyway, the node / edge passes want the threads
     int tx = 4;
     while (tx < 32 && tx < w) tx <<= 1;
     if (tx > nt) tx = nt;
