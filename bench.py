@@ -210,11 +210,14 @@ def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     from dfdm_b200 import _lib
     from dfdm_b200.engine import Plan, GoalProgram, Evaluator
-    from dfdm_b200.distributed import gather_designs, PeerGather
+    from dfdm_b200.distributed import gather_designs, PeerGather, bind_to_gpu_cpus
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpus = None
     if world > 1:
+        if os.environ.get("DFDM_BIND_NUMA", "1") != "0":             # host buffers of a rank on the NUMA node of its GPU
+            cpus = bind_to_gpu_cpus(local_rank)
         dist.init_process_group("nccl", device_id=device)
     batch = args.batch or DEFAULT_BATCH.get(args.workload, 256)
     wl = make_workload(args.workload, batch * world)
@@ -350,7 +353,8 @@ def gpu_arm(args, rank, world, local_rank):
                        "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients%s)" % (world, ": peer stores over NVLink" if peer else (": NCCL" if world > 1 else "")),
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
-                       "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same},
+                       "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same,
+                       "cpu_binding": ("%d cores next to the GPU" % len(cpus)) if cpus else "none"},
             "clocks": clocks,
             "e2e": {"value": batch * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world, "api": "dfdm_loss_and_grad_host (pinned host buffers)"},

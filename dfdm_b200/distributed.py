@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard", "gather_designs", "ensemble_mean", "ShardedBatch", "PeerGather"]
+__all__ = ["shard_bounds", "shard", "gather_designs", "ensemble_mean", "ShardedBatch", "PeerGather", "bind_to_gpu_cpus"]
 
 
 def shard_bounds(batch, world_size, rank):
@@ -210,3 +210,27 @@ class PeerGather:
         for own in self._own:
             self._lib.lib.dfdm_peer_free(self._C.c_void_p(own))
         self._peers, self._own, self._views = [], [], []
+
+
+def bind_to_gpu_cpus(device_index):
+    """
+    Pin this process to the CPU cores next to its GPU (NVML's affinity mask for the device, cut to the cores the
+    process may use).  With one process per GPU on a multi-socket host this keeps pinned host buffers on the GPU's own
+    NUMA node, which is what the host-buffer entry points copy from and to.  Returns the cores, or None when NVML,
+    the device or the platform does not allow it (nothing is changed then).
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = near & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
