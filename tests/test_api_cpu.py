@@ -287,3 +287,49 @@ def test_batched_lbfgs_matches_scipy_on_a_batch_of_bounded_quadratics():
         assert abs(f[b] - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
         assert np.max(np.abs(q[b] - ref.x)) < 1e-4
     assert np.all(q >= -0.3) and np.all(q <= 0.5)
+
+
+def test_bind_to_gpu_cpus_changes_nothing_without_a_gpu():
+    from dfdm_b200.distributed import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_cpus(0) is None
+    assert os.sched_getaffinity(0) == before
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference`: one JSON line on stdout with the keys the driver reads, timed on the host cores."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "pillow",
+                          "--cpu-budget", "1", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "equilibrium+VJP evals/sec" and line["unit"] == "evals/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"] == "pillow"
+
+
+def test_coarse_cycle_bytes_counts_every_visit():
+    """bench.py's algorithmic bytes of the coarse levels: V-cycle = one down + one up per level; W levels double the visits below."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from dfdm_b200 import workloads as W
+    from dfdm_b200.engine import Plan
+    edges, fixed, xyz, loads, q = W.grid_arrays(64)
+    plan = Plan(len(fixed), edges, fixed)
+    from dfdm_b200 import _lib
+    rows = [int(v) for v in plan.array(_lib.ARR_MG_ROWS)]
+    nnzs = [int(v) for v in plan.array(_lib.ARR_MG_NNZ)]
+    v = bench.coarse_cycle_bytes(plan, -1)
+    want = sum(8.0 * nnzs[l] + 64.0 * rows[l] + 24.0 * rows[l + 1] for l in range(1, len(rows) - 1)) + 4.0 * rows[-1] ** 2 + 24.0 * rows[-1]
+    assert abs(v - want) < 1e-6 * want
+    assert bench.coarse_cycle_bytes(plan, 1) > 1.9 * v - 1e-9 or len(rows) < 3          # level 1 and everything below it twice
+    assert bench.coarse_cycle_bytes(plan, 0) == bench.coarse_cycle_bytes(plan, 3)       # 0 means the default depth
