@@ -22,7 +22,7 @@ PRECONDS = {"auto": 0, "jacobi": 1, "multigrid": 2}
 
 ARR_FREE, ARR_FIXED, ARR_FREEFIXED, ARR_ROWPTR, ARR_COLIDX, ARR_EDGE_SLOTS, ARR_SOLVER_PERM = range(7)
 ARR_NODE_INC_PTR, ARR_NODE_INC_EDGE, ARR_NODE_INC_SIGN = 7, 8, 9
-ARR_MG_ROWS, ARR_MG_NNZ = 10, 11
+ARR_MG_ROWS, ARR_MG_NNZ, ARR_PCG_PERM, ARR_MG_AGG = 10, 11, 12, 100
 FLAG_SPMV_MATRIX_FREE = 1
 
 GOAL_KINDS = {"NodePoint": 0, "NodeLine": 1, "NodePlane": 2, "NodeResidualForce": 3, "NodeResidualVector": 4,

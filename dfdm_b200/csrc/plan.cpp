@@ -567,7 +567,14 @@ const int32_t* dfdm_plan_array(const dfdm_plan* plan, int32_t which, int64_t* le
         case DFDM_ARR_NODE_INC_SIGN: v = &plan->ninc_sign; break;
         case DFDM_ARR_MG_ROWS: v = &plan->mg_rows; break;
         case DFDM_ARR_MG_NNZ: v = &plan->mg_nnz; break;
-        default: dfdm::set_error("dfdm_plan_array: unknown array id"); return nullptr;
+        case DFDM_ARR_PCG_PERM: v = &plan->pg_perm; break;
+        default:
+            if (which >= DFDM_ARR_MG_AGG && which < DFDM_ARR_MG_AGG + (int32_t)plan->mg.size()) {
+                v = &plan->mg[which - DFDM_ARR_MG_AGG].agg;
+                break;
+            }
+            dfdm::set_error("dfdm_plan_array: unknown array id");
+            return nullptr;
     }
     if (length) *length = (int64_t)v->size();
     return v->data();

@@ -112,6 +112,9 @@ typedef struct dfdm_plan_info {
 #define DFDM_ARR_NODE_INC_SIGN 9 /* int32[2E]: C[e, node] = -1 (tail u) or +1 (head v); model.py:23,34 */
 #define DFDM_ARR_MG_ROWS 10      /* int32[mg_levels+1]: rows of every multigrid level, level 0 = n_free (empty without a hierarchy) */
 #define DFDM_ARR_MG_NNZ 11       /* int32[mg_levels+1]: stored entries of every level's operator */
+#define DFDM_ARR_PCG_PERM 12     /* int32[n_free]: free index of every row in the PCG path's hierarchical row order */
+#define DFDM_ARR_MG_AGG 100      /* + l (0 <= l < mg_levels): int32[rows of level l], row of level l -> its aggregate on level l+1,
+                                    rows in the PCG path's order; lets a host reference rebuild the hierarchy (tests) */
 
 DFDM_API const char* dfdm_last_error(void);
 DFDM_API int32_t dfdm_abi_version(void);
