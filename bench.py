@@ -210,7 +210,7 @@ def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     from dfdm_b200 import _lib
     from dfdm_b200.engine import Plan, GoalProgram, Evaluator
-    from dfdm_b200.distributed import gather_designs, PeerGather, bind_to_gpu_cpus
+    from dfdm_b200.distributed import ShardedBatch, gather_designs, bind_to_gpu_cpus
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -220,6 +220,10 @@ def gpu_arm(args, rank, world, local_rank):
             cpus = bind_to_gpu_cpus(local_rank)
         dist.init_process_group("nccl", device_id=device)
     batch = args.batch or DEFAULT_BATCH.get(args.workload, 256)
+    if args.scaling == "strong":                                   # fixed global batch, cut across the ranks
+        if batch % world:
+            raise SystemExit("--scaling strong needs a batch divisible by the number of GPUs")
+        batch //= world
     wl = make_workload(args.workload, batch * world)
 
     cpu = None
@@ -233,7 +237,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w, flags=(_lib.FLAG_SPMV_MATRIX_FREE if args.spmv_matrix_free else 0))
+                   pcg_rtol=args.pcg_rtol, pcg_rtol_adjoint=args.pcg_rtol_adjoint, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w, flags=(_lib.FLAG_SPMV_MATRIX_FREE if args.spmv_matrix_free else 0))
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -241,29 +245,25 @@ def gpu_arm(args, rank, world, local_rank):
     if args.steps <= 0:
         args.steps = 3 if solver == "pcg" else 50
 
-    # the one exchange of a batched evaluation: losses and gradients of every design on every rank.  Peer stores over
-    # NVLink (one kernel per tensor + a one-element all-reduce as the fence) when the ranks can map each other's
-    # memory, NCCL all-gather otherwise (DFDM_PEER_GATHER=0 forces it).
-    peer = None
-    if world > 1 and os.environ.get("DFDM_PEER_GATHER", "1") != "0" and PeerGather.available(batch * world):
-        try:
-            peer = (PeerGather(batch * world, (), device=device), PeerGather(batch * world, (E,), device=device))
-        except Exception as exc:                                    # no peer access on this box: NCCL does the same job
-            print("bench.py: peer gather unavailable (%s); using NCCL all-gather" % exc, file=sys.stderr)
-            peer = None
+    # the one exchange of a batched evaluation, named by what the consumer needs (--exchange):
+    #   allgather  losses and gradients of every design on every rank - peer stores over NVLink, every piece of the local
+    #              slice pushed under the kernels of the next piece (--chunks), NCCL when the ranks cannot map each other
+    #              (DFDM_PEER_GATHER=0 forces NCCL)
+    #   root       rank 0 only receives them (a host-side optimiser on one rank)
+    #   losses     gradients stay with their designs, all losses everywhere (a sharded optimiser: B doubles on the wire)
+    #   mean       ensemble mean of loss and gradient: one all-reduce of E + 1 doubles
+    def evaluate(q_local):
+        out = ev.loss_and_grad(prog, q_local)
+        last["out"] = out
+        return out["loss"], out["dq"]
+
+    last = {}
+    sharded = ShardedBatch(evaluate, peer=os.environ.get("DFDM_PEER_GATHER", "1") != "0", exchange=args.exchange,
+                           zero_copy=True, chunks=args.chunks if world > 1 else 1)
 
     def step():
-        out = ev.loss_and_grad(prog, q_dev)
-        if world > 1:
-            if peer:
-                loss_all = peer[0].gather(out["loss"], sync=False)
-                dq_all = peer[1].gather(out["dq"], sync=False)
-                peer[1].fence()
-            else:
-                loss_all = gather_designs(out["loss"], batch * world)
-                dq_all = gather_designs(out["dq"], batch * world)
-            return out, loss_all, dq_all
-        return out, out["loss"], out["dq"]
+        loss_x, dq_x = sharded.loss_and_grad_local(q_dev, batch * world)
+        return last["out"], loss_x, dq_x
 
     working_set = _lib.lib.dfdm_workspace_bytes(plan.handle, batch, None) if solver == "pcg" else batch * E * 8 * 12
     flush = working_set < 2 * L2_BYTES
@@ -271,11 +271,15 @@ def gpu_arm(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None      # sampled from the warm-up on: short steps last < 200 ms
     for _ in range(args.warmup):
-        out, _, _ = step()
+        out, loss_x, dq_x = step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    out = ev.loss_and_grad(prog, q_dev)                            # the whole local slice in one call: status, reference for e2e
     status = out["status"].cpu().numpy()
+    gather_ok = None
+    if world > 1:
+        gather_ok = exchange_check(args.exchange, world, rank, batch, sharded.last_local, loss_x, dq_x, device)
     iters = _lib.last_pcg_iterations() if solver == "pcg" else (0, 0)
 
     # ---- timed regions: device-resident inputs -------------------------------------------------------
@@ -345,19 +349,23 @@ def gpu_arm(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     nf, nnz = plan.n_free, plan.nnz
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
-                       "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]}, "pcg_rtol": args.pcg_rtol or 1e-12,
+                       "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]},
+                       "pcg_rtol": args.pcg_rtol or _lib.PCG_RTOL_DEFAULT, "pcg_rtol_adjoint": args.pcg_rtol_adjoint or _lib.PCG_RTOL_ADJOINT_DEFAULT,
+                       "pcg_rtol_note": "loosest stop tests that keep coordinates within 1e-10 and gradients within 1e-8 of SuperLU at this size (tools/rtol_sweep.py, profiles/)",
                        "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
-                       "parallelism": "dp%d (designs sharded, one all-gather of losses and gradients%s)" % (world, ": peer stores over NVLink" if peer else (": NCCL" if world > 1 else "")),
+                       "parallelism": "dp%d (designs sharded; exchange per step: %s)" % (world, sharded.collective if world > 1 else "none"),
+                       "exchange": args.exchange if world > 1 else None, "gather_ok": gather_ok,
                        "cache": "L2 flushed between steps" if flush else "per-step working set %.1f GB >> 126 MB L2" % (working_set / 1e9),
                        "status_ok": bool(np.all(status == 0)), "e2e_matches_device": same,
                        "cpu_binding": ("%d cores next to the GPU" % len(cpus)) if cpus else "none"},
             "clocks": clocks,
             "e2e": {"value": batch * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
-                    "d2h_bytes_per_step": int(d2h) * world, "api": "dfdm_loss_and_grad_host (pinned host buffers)"},
+                    "d2h_bytes_per_step": int(d2h) * world,
+                    "api": "dfdm_loss_and_grad_host (pinned host buffers; the batch is cut into chunks whose copies run under the kernels of the neighbouring chunk)"},
             "gpu_launches": launches}
     if solver == "pcg" and sum(prof_count) > 0:
         nc = plan.info.get("mg_n_coarse", 0)
@@ -381,21 +389,37 @@ def gpu_arm(args, rank, world, local_rank):
                 avg_ms = prof_ms[k] / prof_count[k]
                 kernels.append({"kernel": name, "launches": prof_count[k], "avg_ms": avg_ms, "share_of_step": prof_ms[k] / ms_profiled,
                                 "algorithmic_bytes": alg[name], "achieved_gbs": alg[name] / (avg_ms * 1e-3) / 1e9})
-        # the dominant single kernel; the coarse levels are a group of ~20 small launches, reported under 'kernels' and 'iteration'
-        top = max((kk for kk in kernels if kk["algorithmic_bytes"] > 0 and kk["kernel"].startswith("k_")), key=lambda kk: kk["share_of_step"])
-        line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": top["achieved_gbs"] / peak, "traffic": traffic_for(top["kernel"], wl["name"]),
-                            "peak_source": peak_src, "timing": "CUDA events on the launch stream after every PCG launch, over a second timed region of the same K steps",
-                            "ms_per_step_with_events": ms_profiled / args.steps}
-        line["kernels"] = kernels
         once = ("k_assemble", "state, loss and reverse edge kernels (5 launches)")      # these run once per evaluation
         per_iteration = [kk for kk in kernels if kk["kernel"] not in once]
         it_ms = sum(kk["avg_ms"] for kk in per_iteration)
         it_bytes = sum(kk["algorithmic_bytes"] for kk in per_iteration)
+        # the WHOLE step against the roofline: algorithmic bytes of everything a step launches / ms_per_step of the
+        # un-instrumented region.  Per solve: k_pcg_init (r, 1/diag in; x, p out: 80 n_f), one preconditioner cycle and
+        # one direction pass without the x update (60 n_f) before the first iteration, then the iterations.
+        n_iter = iters[0] + iters[1]
+        cyc = alg["k_mg_down[level 0]"] + alg["k_mg_up[level 0]"] + alg["multigrid coarse levels (per V-cycle)"] if is_mg else 0.0
+        step_parts = {"pcg iterations (%d forward + %d adjoint)" % iters: n_iter * it_bytes,
+                      "solver start (init, first cycle, first direction) x 2": 2 * (80.0 * nf * batch + cyc + 60.0 * nf * batch),
+                      "k_assemble": alg["k_assemble"], "state, loss and reverse edge kernels": alg["state, loss and reverse edge kernels (5 launches)"],
+                      "hierarchy set-up (single-precision copies, Galerkin sums)": mg_setup_bytes(plan) * batch if is_mg else 0.0,
+                      "k_edge_dq": (40.0 * E + 24.0 * plan.n) * batch, "layout changes of q and dq": 32.0 * E * batch}
+        step_bytes = sum(step_parts.values())
+        ms_step = ms_total / args.steps
+        top = max((kk for kk in kernels if kk["algorithmic_bytes"] > 0), key=lambda kk: kk["share_of_step"])
+        line["roofline"] = {"bound": "hbm", "kernel": "whole step; dominant group: " + top["kernel"], "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                            "traffic": traffic_for(top["kernel"], wl["name"]), "peak_source": peak_src,
+                            "what": "algorithmic bytes of one whole step (step_bytes) / ms_per_step / peak; per-kernel and per-group numbers under 'kernels'",
+                            "step_bytes": step_bytes, "step_bytes_parts": step_parts,
+                            "dominant": {"kernel": top["kernel"], "share_of_step": top["share_of_step"], "achieved": top["achieved_gbs"],
+                                         "frac": top["achieved_gbs"] / peak},
+                            "timing": "value / ms_per_step: CUDA events around each step, nothing else on the stream; 'kernels': CUDA events after every PCG launch in a second timed region of the same K steps",
+                            "ms_per_step_with_events": ms_profiled / args.steps}
+        line["kernels"] = kernels
         line["roofline"]["iteration"] = {"what": "one whole PCG iteration = the kernels listed under 'kernels' except k_assemble and the state / loss group", "ms": it_ms,
                                          "algorithmic_bytes": it_bytes, "achieved": it_bytes / (it_ms * 1e-3) / 1e9,
                                          "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak, "share_of_step": sum(kk["share_of_step"] for kk in per_iteration)}
-        line["roofline"]["frac_of_nominal_8000"] = top["achieved_gbs"] / 8000.0
+        line["roofline"]["frac_of_nominal_8000"] = line["roofline"]["achieved"] / 8000.0
     else:
         # direct path: one fused kernel per step; mandatory I/O only (q in, loss + dq out)
         alg = batch * (16.0 * E + 8.0)
@@ -431,6 +455,51 @@ def fp64_peak_gflops(device):
         torch.cuda.synchronize()
         best = min(best, s.elapsed_time(e))
     return 2.0 * 4096 ** 3 / (best * 1e-3) / 1e9
+
+
+def exchange_check(mode, world, rank, batch, pieces, loss_x, dq_x, device):
+    """Every row of the exchanged arrays against its owner's copy, bit for bit: the owners' per-row integer checksums
+    travel through NCCL (an independent path) and are compared with checksums of the rows as received."""
+    import torch
+    import torch.distributed as dist
+    out = {"loss": torch.cat([p[0] for p in pieces]), "dq": torch.cat([p[1] for p in pieces])}     # this rank's own rows of that step
+
+    def rowsum(t):                                                  # exact, order-independent: wrap-around integer sums
+        return t.contiguous().view(torch.int64).reshape(t.shape[0], -1).sum(dim=1)
+
+    own = torch.stack([rowsum(out["loss"].reshape(-1, 1)), rowsum(out["dq"])], dim=1)
+    every = torch.empty((world * batch, 2), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(every, own)
+    ok = True
+    if mode == "allgather" or (mode == "root" and rank == 0):
+        ok = bool(torch.equal(rowsum(loss_x.reshape(-1, 1)), every[:, 0])) and bool(torch.equal(rowsum(dq_x), every[:, 1]))
+    elif mode == "losses":
+        ok = bool(torch.equal(rowsum(loss_x.reshape(-1, 1)), every[:, 0])) and bool(torch.equal(rowsum(dq_x), own[:, 1]))
+    elif mode == "mean":
+        packed = torch.cat([out["dq"].sum(dim=0), out["loss"].sum().reshape(1)])
+        dist.all_reduce(packed)
+        packed /= float(world * batch)
+        ok = bool(torch.allclose(dq_x, packed[:-1], rtol=1e-12, atol=0)) and bool(torch.allclose(loss_x, packed[-1], rtol=1e-12, atol=0))
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise SystemExit("bench.py: the exchanged rows differ from their owners' rows (exchange %s)" % mode)
+    return True
+
+
+def mg_setup_bytes(plan):
+    """Algorithmic bytes per design of the numerical set-up of the hierarchy: level 0 reads K (8 nnz) and 1/diag (8 n) and
+    writes two single-precision copies and 1/diag (8 nnz + 4 n); every coarse level sums its parent's values (4 nnz_parent
+    in, 4 nnz out), takes 1/diag (4 n out) and the column-scaled copy (4 nnz in, 4 nnz out)."""
+    from dfdm_b200 import _lib
+    rows = [int(v) for v in plan.array(_lib.ARR_MG_ROWS)]
+    nnzs = [int(v) for v in plan.array(_lib.ARR_MG_NNZ)]
+    if len(rows) < 2:
+        return 0.0
+    total = 16.0 * nnzs[0] + 12.0 * rows[0]
+    for l in range(1, len(rows)):
+        total += 4.0 * nnzs[l - 1] + 12.0 * nnzs[l] + 4.0 * rows[l]
+    return total
 
 
 def coarse_cycle_bytes(plan, mg_w_levels):
@@ -486,7 +555,12 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="designs per GPU (default: the configuration's own)")
     ap.add_argument("--solver", default="auto", choices=["auto", "direct", "pcg"])
     ap.add_argument("--pcg-rtol", type=float, default=0.0)
+    ap.add_argument("--pcg-rtol-adjoint", type=float, default=0.0)
     ap.add_argument("--pcg-check-every", type=int, default=0)
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "root", "losses", "mean"],
+                    help="N > 1: what travels between the ranks after an evaluation (see gpu_arm)")
+    ap.add_argument("--chunks", type=int, default=2, help="N > 1, allgather by peer stores: pieces of the local slice, each pushed under the next one's kernels")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch designs per GPU; strong: --batch designs in all")
     ap.add_argument("--pcg-maxiter", type=int, default=0, help="cap PCG iterations (kernel tuning runs only: results not converged)")
     ap.add_argument("--precond", default="auto", choices=["auto", "jacobi", "multigrid"])
     ap.add_argument("--mg-omega", type=float, default=0.0)

@@ -24,6 +24,7 @@ ARR_FREE, ARR_FIXED, ARR_FREEFIXED, ARR_ROWPTR, ARR_COLIDX, ARR_EDGE_SLOTS, ARR_
 ARR_NODE_INC_PTR, ARR_NODE_INC_EDGE, ARR_NODE_INC_SIGN = 7, 8, 9
 ARR_MG_ROWS, ARR_MG_NNZ, ARR_PCG_PERM, ARR_MG_AGG = 10, 11, 12, 100
 FLAG_SPMV_MATRIX_FREE = 1
+PCG_RTOL_DEFAULT, PCG_RTOL_ADJOINT_DEFAULT = 1e-12, 1e-12     # include/dfdm_b200.h DFDM_PCG_RTOL_*_DEFAULT
 
 GOAL_KINDS = {"NodePoint": 0, "NodeLine": 1, "NodePlane": 2, "NodeResidualForce": 3, "NodeResidualVector": 4,
               "NodeResidualDirection": 5, "EdgeLength": 6, "EdgeForce": 7, "EdgeLoadPath": 8, "EdgeVectorAngle": 9,
@@ -42,7 +43,7 @@ SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan
 class Options(C.Structure):
     _fields_ = [("solver", C.c_int32), ("pcg_maxiter", C.c_int32), ("pcg_rtol", C.c_double),
                 ("pcg_check_every", C.c_int32), ("pcg_precond", C.c_int32), ("mg_omega", C.c_double), ("mg_over", C.c_double),
-                ("mg_w_levels", C.c_int32), ("flags", C.c_int32), ("mg_over_w", C.c_double)]
+                ("mg_w_levels", C.c_int32), ("flags", C.c_int32), ("mg_over_w", C.c_double), ("pcg_rtol_adjoint", C.c_double)]
 
 
 class PlanInfo(C.Structure):
@@ -94,7 +95,7 @@ def _load():
     lib.dfdm_peer_push.argtypes = [vp, i64, i64, C.POINTER(vp), i32, vp]
     for name in SYMBOLS:
         getattr(lib, name)
-    if lib.dfdm_abi_version() != 2:
+    if lib.dfdm_abi_version() != 3:
         raise ImportError("dfdm_b200: ABI version mismatch between _lib.py and libdfdm_b200.so")
     return lib
 
@@ -108,13 +109,13 @@ def check(rc):
 
 
 def make_options(solver="auto", pcg_maxiter=0, pcg_rtol=0.0, pcg_check_every=0, pcg_precond="auto", mg_omega=0.0, mg_over=0.0,
-                 mg_w_levels=0, mg_over_w=0.0, flags=0):
+                 mg_w_levels=0, mg_over_w=0.0, flags=0, pcg_rtol_adjoint=0.0):
     if isinstance(solver, str):
         solver = SOLVERS[solver]
     if isinstance(pcg_precond, str):
         pcg_precond = PRECONDS[pcg_precond]
     return Options(solver, int(pcg_maxiter), float(pcg_rtol), int(pcg_check_every), int(pcg_precond), float(mg_omega), float(mg_over),
-                   int(mg_w_levels), int(flags), float(mg_over_w))
+                   int(mg_w_levels), int(flags), float(mg_over_w), float(pcg_rtol_adjoint))
 
 
 def plan_array(handle, which):

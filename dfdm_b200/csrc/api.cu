@@ -1,4 +1,5 @@
 // C ABI (include/dfdm_b200.h): plan / goal-program lifetime, device mirrors, dispatch.
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -168,10 +169,13 @@ static int dispatch(const dfdm_plan* plan, const dfdm_goalprog* prog, Eval& ev, 
     return solver == DFDM_SOLVER_DIRECT ? run_direct(ev) : run_pcg(ev);
 }
 
-// cached device arena for the *_host entry points
-static int arena_get(const Plan& P, int device, int64_t bytes, char** out) {
+// cached per-device arena of the *_host entry points (created on first use; the caller holds `busy` while it uses it)
+static Plan::Arena& arena_ref(const Plan& P, int device) {
     std::lock_guard<std::mutex> lock(P.mu);
-    Plan::Arena& a = P.arena[device];
+    return P.arena[device];
+}
+
+static int arena_prepare(Plan::Arena& a, int64_t bytes) {
     if (a.bytes < bytes) {
         if (a.ptr) cudaFree(a.ptr);
         a.ptr = nullptr;
@@ -179,8 +183,39 @@ static int arena_get(const Plan& P, int device, int64_t bytes, char** out) {
         DFDM_CUDA_OK(cudaMalloc(&a.ptr, (size_t)bytes));
         a.bytes = bytes;
     }
-    *out = static_cast<char*>(a.ptr);
+    for (int k = 0; k < 3; ++k)
+        if (!a.stream[k]) {
+            cudaStream_t st = nullptr;
+            DFDM_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            a.stream[k] = st;
+        }
+    for (int k = 0; k < Plan::kHostChunksMax; ++k) {
+        if (!a.ev_in[k]) {
+            cudaEvent_t e = nullptr;
+            DFDM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            a.ev_in[k] = e;
+        }
+        if (!a.ev_done[k]) {
+            cudaEvent_t e = nullptr;
+            DFDM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            a.ev_done[k] = e;
+        }
+    }
     return DFDM_OK;
+}
+
+// How a host call splits its batch: the copies of chunk k+1 (in) and chunk k-1 (out) run under the kernels of chunk k,
+// so only the first chunk's way in and the last chunk's way out are exposed.  Chunks are multiples of 32 designs where
+// the batch allows, so every chunk keeps whole warps of design lanes.  DFDM_HOST_CHUNKS overrides the count (tuning).
+static int host_chunks(int B, bool pcg, int* b0 /* [kHostChunksMax + 1] */) {
+    static const int forced = std::getenv("DFDM_HOST_CHUNKS") ? std::atoi(std::getenv("DFDM_HOST_CHUNKS")) : 0;
+    int k = forced > 0 ? forced : (pcg ? (B >= 128 ? 2 : 1) : (B >= 512 ? 4 : 1));
+    k = std::max(1, std::min(std::min(k, Plan::kHostChunksMax), B));
+    const int unit = B >= 64 * k ? 32 : (B >= 4 * k ? 2 : 1);
+    const int units = (B + unit - 1) / unit;
+    for (int c = 0; c <= k; ++c) b0[c] = std::min(B, (int)(((int64_t)units * c / k) * unit));
+    b0[k] = B;
+    return k;
 }
 
 }  // namespace dfdm
@@ -215,11 +250,17 @@ void dfdm_plan_destroy(dfdm_plan* plan) {
         cudaSetDevice(prev);
     }
     for (auto& kv : plan->arena) {
-        if (!kv.second.ptr) continue;
         int prev = 0;
         cudaGetDevice(&prev);
         cudaSetDevice(kv.first);
-        cudaFree(kv.second.ptr);
+        Plan::Arena& a = kv.second;
+        if (a.ptr) cudaFree(a.ptr);
+        for (void* st : a.stream)
+            if (st) cudaStreamDestroy(static_cast<cudaStream_t>(st));
+        for (int k = 0; k < Plan::kHostChunksMax; ++k) {
+            if (a.ev_in[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_in[k]));
+            if (a.ev_done[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_done[k]));
+        }
         cudaSetDevice(prev);
     }
     delete plan;
@@ -378,11 +419,19 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     int device = 0;
     DFDM_CUDA_OK(cudaGetDevice(&device));
     const int64_t n = plan->n, E = plan->E, nx = plan->nx;
-    int64_t ws_bytes = dfdm_workspace_bytes(plan, B, options);
+    int solver = 0;
+    int rc = resolve_solver(*plan, options, solver);
+    if (rc) return rc;
+    int cb[Plan::kHostChunksMax + 1];
+    const int nchunks = host_chunks(B, solver == DFDM_SOLVER_PCG, cb);
+    int widest = 0;
+    for (int c = 0; c < nchunks; ++c) widest = std::max(widest, cb[c + 1] - cb[c]);
+    int64_t ws_bytes = dfdm_workspace_bytes(plan, widest, options);
     if (ws_bytes < 0) return (int)ws_bytes;
-    Bump io(nullptr);
-    auto layout = [&](Bump& bump, double*& d_q, double*& d_loads, double*& d_xfix, double*& d_loss, double*& d_dq, double*& d_xyz,
-                      double*& d_res, double*& d_vec, double*& d_len, double*& d_for, int32_t*& d_status, char*& d_ws) {
+    double *d_q, *d_loads, *d_xfix, *d_loss, *d_dq, *d_xyz, *d_res, *d_vec, *d_len, *d_for;
+    int32_t* d_status;
+    char* d_ws;
+    auto layout = [&](Bump& bump) {
         d_q = bump.take<double>(B * E);
         d_loads = bump.take<double>(n * 3);
         d_xfix = bump.take<double>(std::max<int64_t>(nx * 3, 1));
@@ -396,34 +445,56 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
         d_status = bump.take<int32_t>(B);
         d_ws = bump.take<char>(ws_bytes);
     };
-    double *d_q, *d_loads, *d_xfix, *d_loss, *d_dq, *d_xyz, *d_res, *d_vec, *d_len, *d_for;
-    int32_t* d_status;
-    char* d_ws;
-    layout(io, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws);
-    char* base = nullptr;
-    int rc = arena_get(*plan, device, io.off, &base);
+    Bump count(nullptr);
+    layout(count);
+    Plan::Arena& A = arena_ref(*plan, device);
+    std::lock_guard<std::mutex> busy(A.busy);              // the arena and its streams belong to this call until it returns
+    rc = arena_prepare(A, count.off);
     if (rc) return rc;
-    Bump real(base);
-    layout(real, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws);
-    cudaStream_t st = nullptr;
-    DFDM_CUDA_OK(cudaMemcpyAsync(d_q, q, sizeof(double) * B * E, cudaMemcpyHostToDevice, st));
-    DFDM_CUDA_OK(cudaMemcpyAsync(d_loads, loads, sizeof(double) * n * 3, cudaMemcpyHostToDevice, st));
-    if (nx > 0) DFDM_CUDA_OK(cudaMemcpyAsync(d_xfix, xyz_fixed, sizeof(double) * nx * 3, cudaMemcpyHostToDevice, st));
-    if (prog)
-        rc = dfdm_loss_and_grad(plan, prog, B, d_q, d_loads, d_xfix, d_loss, d_dq, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws,
-                                ws_bytes, options, st);
-    else
-        rc = dfdm_forward(plan, B, d_q, d_loads, d_xfix, d_xyz, d_res, d_vec, d_len, d_for, d_status, d_ws, ws_bytes, options, st);
+    Bump real(static_cast<char*>(A.ptr));
+    layout(real);
+    cudaStream_t s_in = static_cast<cudaStream_t>(A.stream[0]), s_cmp = static_cast<cudaStream_t>(A.stream[1]),
+                 s_out = static_cast<cudaStream_t>(A.stream[2]);
+    // way in: the design-independent arrays, then q chunk by chunk
+    DFDM_CUDA_OK(cudaMemcpyAsync(d_loads, loads, sizeof(double) * n * 3, cudaMemcpyHostToDevice, s_in));
+    if (nx > 0) DFDM_CUDA_OK(cudaMemcpyAsync(d_xfix, xyz_fixed, sizeof(double) * nx * 3, cudaMemcpyHostToDevice, s_in));
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t b0 = cb[c], nb = cb[c + 1] - cb[c];
+        DFDM_CUDA_OK(cudaMemcpyAsync(d_q + b0 * E, q + b0 * E, sizeof(double) * nb * E, cudaMemcpyHostToDevice, s_in));
+        DFDM_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(A.ev_in[c]), s_in));
+    }
+    auto at = [](double* p, int64_t off) { return p ? p + off : nullptr; };
+    for (int c = 0; c < nchunks && rc == DFDM_OK; ++c) {
+        const int64_t b0 = cb[c], nb = cb[c + 1] - cb[c];
+        DFDM_CUDA_OK(cudaStreamWaitEvent(s_cmp, static_cast<cudaEvent_t>(A.ev_in[c]), 0));
+        if (prog)
+            rc = dfdm_loss_and_grad(plan, prog, (int32_t)nb, d_q + b0 * E, d_loads, d_xfix, d_loss + b0, at(d_dq, b0 * E),
+                                    at(d_xyz, b0 * n * 3), at(d_res, b0 * n * 3), at(d_vec, b0 * E * 3), at(d_len, b0 * E),
+                                    at(d_for, b0 * E), d_status + b0, d_ws, ws_bytes, options, s_cmp);
+        else
+            rc = dfdm_forward(plan, (int32_t)nb, d_q + b0 * E, d_loads, d_xfix, at(d_xyz, b0 * n * 3), at(d_res, b0 * n * 3),
+                              at(d_vec, b0 * E * 3), at(d_len, b0 * E), at(d_for, b0 * E), d_status + b0, d_ws, ws_bytes, options, s_cmp);
+        if (rc) break;
+        DFDM_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(A.ev_done[c]), s_cmp));
+        // way out of this chunk, under the kernels of the next one
+        DFDM_CUDA_OK(cudaStreamWaitEvent(s_out, static_cast<cudaEvent_t>(A.ev_done[c]), 0));
+        auto back = [&](double* host, const double* dev, int64_t per_design) -> int {
+            if (host) DFDM_CUDA_OK(cudaMemcpyAsync(host + b0 * per_design, dev + b0 * per_design, sizeof(double) * nb * per_design,
+                                                   cudaMemcpyDeviceToHost, s_out));
+            return DFDM_OK;
+        };
+        if ((rc = back(loss, d_loss, 1)) || (rc = back(dq, d_dq, E)) || (rc = back(xyz, d_xyz, n * 3)) ||
+            (rc = back(residuals, d_res, n * 3)) || (rc = back(vectors, d_vec, E * 3)) || (rc = back(lengths, d_len, E)) ||
+            (rc = back(forces, d_for, E)))
+            break;
+        if (status) DFDM_CUDA_OK(cudaMemcpyAsync(status + b0, d_status + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
+    }
+    // the arena is released (and may be reused by another thread) on return: nothing of this call may still be in flight
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
     if (rc) return rc;
-    if (loss) DFDM_CUDA_OK(cudaMemcpyAsync(loss, d_loss, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    if (dq) DFDM_CUDA_OK(cudaMemcpyAsync(dq, d_dq, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
-    if (xyz) DFDM_CUDA_OK(cudaMemcpyAsync(xyz, d_xyz, sizeof(double) * B * n * 3, cudaMemcpyDeviceToHost, st));
-    if (residuals) DFDM_CUDA_OK(cudaMemcpyAsync(residuals, d_res, sizeof(double) * B * n * 3, cudaMemcpyDeviceToHost, st));
-    if (vectors) DFDM_CUDA_OK(cudaMemcpyAsync(vectors, d_vec, sizeof(double) * B * E * 3, cudaMemcpyDeviceToHost, st));
-    if (lengths) DFDM_CUDA_OK(cudaMemcpyAsync(lengths, d_len, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
-    if (forces) DFDM_CUDA_OK(cudaMemcpyAsync(forces, d_for, sizeof(double) * B * E, cudaMemcpyDeviceToHost, st));
-    if (status) DFDM_CUDA_OK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-    DFDM_CUDA_OK(cudaStreamSynchronize(st));
+    DFDM_CUDA_OK(e1);
+    DFDM_CUDA_OK(e2);
+    DFDM_CUDA_OK(e3);
     return DFDM_OK;
 }
 

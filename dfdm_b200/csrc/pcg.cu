@@ -1,4 +1,5 @@
-// Large-network path: Jacobi-preconditioned CG on a batch-interleaved CSR, all designs in lock step.
+// Large-network path: conjugate gradients on a batch-interleaved CSR, all designs in lock step, preconditioned by one
+// cycle of plain-aggregation multigrid (default) or by the diagonal (Jacobi).
 //
 // Layout: every per-design array is stored element-major with the batch innermost, A[elem][B], so a
 // warp that works on one row / edge for 32 consecutive designs reads and writes 256 contiguous bytes
@@ -55,7 +56,7 @@ struct PcgScalars {
     double* alpha;
     double* beta;
     double* bb;       // ||b||^2
-    int32_t* frozen;  // [3][B] converged (or zero right-hand side): alpha forced to 0
+    int32_t* frozen;  // [3][B] != 0: alpha forced to 0.  1 converged (or zero right-hand side), 2 non-finite, 3 breakdown
     int32_t* n_active;   // [0] columns not yet converged (live); [1], [2] snapshots by iteration parity: kernels of iteration k
                          // read [1 + par] (written during iteration k-1) and the direction kernel writes [1 + (par ^ 1)], so no
                          // kernel ever reads a snapshot that a concurrently running CTA may be writing
@@ -284,15 +285,17 @@ __device__ bool publish_vec(const double (&v)[NV], const LaneCfg& cfg, int B, do
 // x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                          const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
-                                                         PcgScalars S, int mg) {
+                                                         PcgScalars S, int mg, const int32_t* __restrict__ keep) {
+    // keep (fallback run only): columns that the previous attempt converged stay frozen and keep their solution
     VEC_SETUP();
     double v[2] = {0, 0};
     if (live) {
+        const bool kept = keep && keep[c * B + b] == 1;
         for (int f = row0; f < nf; f += rstride) {
             size_t o = ((size_t)f * 3 + c) * B + b;
             double rc = r[o];
             double z = rc * dinv[(size_t)f * B + b];
-            x[o] = 0.0;
+            if (!kept) x[o] = 0.0;
             p[o] = mg ? 0.0 : z;             // multigrid: the first direction comes from the V-cycle
             v[0] += rc * z;
             v[1] += rc * rc;
@@ -308,8 +311,9 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
             S.rho[cc * B + b2] = rho;
             S.bb[cc * B + b2] = bb;
             S.beta[cc * B + b2] = 0.0;
-            int frozen = (bb == 0.0 || !(rho != 0.0)) ? 1 : 0;     // zero right-hand side: x = 0 is exact
-            (void)mg;
+            int frozen = bb == 0.0 ? 1 : 0;                        // zero right-hand side: x = 0 is exact
+            if (!frozen && !mg && !(rho != 0.0)) frozen = 3;       // r . D^-1 r = 0 with r != 0 (indefinite diagonal): breakdown
+            if (keep && keep[cc * B + b2] == 1) frozen = 1;
             S.frozen[cc * B + b2] = frozen;
             fresh += frozen ? 0 : 1;
         }
@@ -1265,7 +1269,7 @@ __global__ void k_pcg_status(int B, const int32_t* __restrict__ frozen, int32_t*
     if (b >= B) return;
     int f0 = frozen[b], f1 = frozen[B + b], f2 = frozen[2 * B + b];
     int now = (f0 == 2 || f1 == 2 || f2 == 2) ? DFDM_STATUS_NONFINITE
-            : ((f0 && f1 && f2) ? DFDM_STATUS_OK : DFDM_STATUS_NOT_CONVERGED);
+            : ((f0 == 1 && f1 == 1 && f2 == 1) ? DFDM_STATUS_OK : DFDM_STATUS_NOT_CONVERGED);
     int prev = accumulate ? status[b] : DFDM_STATUS_OK;
     status[b] = prev != DFDM_STATUS_OK ? prev : now;
 }
@@ -1554,7 +1558,8 @@ struct MgBuffers {
 
 struct PcgBuffers {
     MgBuffers mg;
-    double *qT, *vals, *dinv, *xs, *r, *p, *Ap, *rhs_keep;
+    double *qT, *vals, *dinv, *xs, *r, *p, *Ap;
+    int32_t* keep;         // [3][B] columns converged by the multigrid attempt (Jacobi fallback only)
     double *X, *R, *U, *L, *F, *Xb, *Rb, *Ub, *dqT;
     double *cX, *cR, *cU, *cL, *cF;
     double *lp_partial, *pn, *pe, *lpbar, *net_loss;
@@ -1594,7 +1599,7 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
     w.r = bump.take<double>(nf * 3 * B);
     w.p = bump.take<double>(nf * 3 * B);
     w.Ap = bump.take<double>(nf * 3 * B);
-    w.rhs_keep = bump.take<double>(mg_levels > 0 ? nf * 3 * B : 0);
+    w.keep = bump.take<int32_t>(3 * B);
     w.X = bump.take<double>(n * 3 * B);
     w.R = bump.take<double>(n * 3 * B);
     w.U = bump.take<double>(E * 3 * B);
@@ -1952,30 +1957,33 @@ static int mg_vcycle(const PlanDev& P, const MgDev& M, const LaneCfg& base, int 
 }
 
 static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
-                          cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap);
+                          double rtol, cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap, const int32_t* keep);
 
 // Solve K x = r for all designs.  The multigrid preconditioner is tried first with a generous iteration cap; should it
-// fail to converge (an over-corrected cycle can lose definiteness on unusual networks), the right-hand side is restored
-// and the solve is repeated with the Jacobi preconditioner, which is definite whenever K is.
+// fail to converge (an over-corrected cycle can lose definiteness on unusual networks), `restore_rhs` rebuilds the
+// right-hand side in w.r (nothing is copied on the way in: the fallback never fires on ordinary networks) and the solve
+// is repeated with the Jacobi preconditioner, which is definite whenever K is.  Columns the first attempt converged keep
+// their solution and stay frozen in the second.
+template <typename Restore>
 static int pcg_solve(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
-                     cudaStream_t st, int32_t* host_flag, int* iters_out) {
+                     double rtol, cudaStream_t st, int32_t* host_flag, int* iters_out, Restore restore_rhs) {
     const bool mg = M != nullptr && M->n_levels > 0;
-    if (!mg) return pcg_solve_once(P, nullptr, base, B, w, opt, st, host_flag, iters_out, 0);
-    const size_t bytes = sizeof(double) * (size_t)P.nf * 3 * B;
-    DFDM_CUDA_OK(cudaMemcpyAsync(w.rhs_keep, w.r, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!mg) return pcg_solve_once(P, nullptr, base, B, w, opt, rtol, st, host_flag, iters_out, 0, nullptr);
     const int cap = opt.pcg_maxiter > 0 ? std::min(opt.pcg_maxiter, 400) : 400;
-    int rc = pcg_solve_once(P, M, base, B, w, opt, st, host_flag, iters_out, cap);
+    int rc = pcg_solve_once(P, M, base, B, w, opt, rtol, st, host_flag, iters_out, cap, nullptr);
     if (rc || *host_flag == 0) return rc;
     if (opt.pcg_maxiter > 0 && opt.pcg_maxiter <= cap) return DFDM_OK;      // the caller asked for a short run
-    DFDM_CUDA_OK(cudaMemcpyAsync(w.r, w.rhs_keep, bytes, cudaMemcpyDeviceToDevice, st));
+    DFDM_CUDA_OK(cudaMemcpyAsync(w.keep, w.S.frozen, sizeof(int32_t) * 3 * (size_t)B, cudaMemcpyDeviceToDevice, st));
+    rc = restore_rhs();
+    if (rc) return rc;
     int extra = 0;
-    rc = pcg_solve_once(P, nullptr, base, B, w, opt, st, host_flag, &extra, 0);
+    rc = pcg_solve_once(P, nullptr, base, B, w, opt, rtol, st, host_flag, &extra, 0, w.keep);
     *iters_out += extra;
     return rc;
 }
 
 static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base, int B, PcgBuffers& w, const dfdm_options& opt,
-                          cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap) {
+                          double rtol, cudaStream_t st, int32_t* host_flag, int* iters_out, int iter_cap, const int32_t* keep) {
     const bool mg = M != nullptr && M->n_levels > 0;
     // cycle shape: coarse levels 1 .. w_levels are visited twice (W-cycle); deeper levels once.  Plain aggregation gains
     // most from revisiting the first coarse levels; the tiny ones below are latency bound (8 visits of the cluster kernel
@@ -1994,13 +2002,12 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     int grid = cfg.nchunks * cfg.nslabs;
     int maxiter = opt.pcg_maxiter > 0 ? opt.pcg_maxiter : (int)(20.0 * std::sqrt((double)P.nf)) + 2000;
     if (iter_cap > 0) maxiter = std::min(maxiter, iter_cap);
-    double rtol = opt.pcg_rtol > 0 ? opt.pcg_rtol : 1e-12;
     const int every = opt.pcg_check_every > 0 ? opt.pcg_check_every : 0;       // 0: look-ahead polls (below)
     const float over_w = (float)(opt.mg_over_w > 0 ? opt.mg_over_w : (w_levels > 0 ? kMgOverTwice : (double)mp.over));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
     w.S.par = 0;
-    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0);
+    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0, keep);
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used = 0;
     if (mg) {
@@ -2157,7 +2164,13 @@ int run_pcg(Eval& ev) {
         rc = mg_setup(P, ev.M, cfg, B, w, st);
         if (rc) return rc;
     }
-    rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, st, host_flag, &g_iters[0]);
+    const double rtol_fwd = ev.opt.pcg_rtol > 0 ? ev.opt.pcg_rtol : DFDM_PCG_RTOL_DEFAULT;
+    const double rtol_adj = ev.opt.pcg_rtol_adjoint > 0 ? ev.opt.pcg_rtol_adjoint : DFDM_PCG_RTOL_ADJOINT_DEFAULT;
+    rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, rtol_fwd, st, host_flag, &g_iters[0], [&]() -> int {
+        k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
+        DFDM_LAUNCH_OK("k_assemble");
+        return DFDM_OK;
+    });
     if (rc) return rc;
     if (ev.status) {
         k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 0);
@@ -2204,7 +2217,11 @@ int run_pcg(Eval& ev) {
             DFDM_CUDA_OK(cudaStreamSynchronize(st));
             prof_resolve(post_used);
         }
-        rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, st, host_flag, &g_iters[1]);
+        rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, rtol_adj, st, host_flag, &g_iters[1], [&]() -> int {
+            k_adjoint_rhs<<<grid, kThreads, 0, st>>>(P, cfg, B, w.Xb, w.Ub, w.r);
+            DFDM_LAUNCH_OK("k_adjoint_rhs");
+            return DFDM_OK;
+        });
         if (rc) return rc;
         if (ev.status) {
             k_pcg_status<<<gb, tb, 0, st>>>(B, w.S.frozen, ev.status, 1);

@@ -108,7 +108,17 @@ struct Plan {
     mutable std::map<int, PlanDev> dev;
     mutable std::map<int, PlanDev> dev_pcg;
     mutable std::map<int, void*> dev_block;
-    struct Arena { void* ptr = nullptr; int64_t bytes = 0; };
+    // One per device, for the *_host entry points: device memory, three private streams (copy in, compute, copy out) and
+    // the events that chain them.  `busy` is held for a whole host call: *_host calls on one (plan, device) are serialised.
+    static constexpr int kHostChunksMax = 8;
+    struct Arena {
+        void* ptr = nullptr;
+        int64_t bytes = 0;
+        std::mutex busy;
+        void* stream[3] = {nullptr, nullptr, nullptr};
+        void* ev_in[kHostChunksMax] = {nullptr};
+        void* ev_done[kHostChunksMax] = {nullptr};
+    };
     mutable std::map<int, Arena> arena;
 };
 

@@ -135,14 +135,14 @@ class Evaluator:
     STATE = ("xyz", "residuals", "vectors", "lengths", "forces")
 
     def __init__(self, plan, loads, xyz_fixed, device=None, solver="auto", pcg_rtol=0.0, pcg_maxiter=0, pcg_check_every=0,
-                 pcg_precond="auto", mg_omega=0.0, mg_over=0.0, mg_w_levels=0, mg_over_w=0.0, flags=0):
+                 pcg_precond="auto", mg_omega=0.0, mg_over=0.0, mg_w_levels=0, mg_over_w=0.0, flags=0, pcg_rtol_adjoint=0.0):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("dfdm_b200 evaluates on a CUDA device and there is none here (no CPU fallback)")
         self.torch = torch
         self.plan = plan
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.options = _lib.make_options(solver, pcg_maxiter, pcg_rtol, pcg_check_every, pcg_precond, mg_omega, mg_over, mg_w_levels, mg_over_w, flags)
+        self.options = _lib.make_options(solver, pcg_maxiter, pcg_rtol, pcg_check_every, pcg_precond, mg_omega, mg_over, mg_w_levels, mg_over_w, flags, pcg_rtol_adjoint)
         loads = np.ascontiguousarray(np.asarray(loads, dtype=np.float64).reshape(plan.n, 3))
         xyz_fixed = np.ascontiguousarray(np.asarray(xyz_fixed, dtype=np.float64).reshape(plan.n_fixed, 3))
         self.loads_host, self.xyz_fixed_host = loads, xyz_fixed

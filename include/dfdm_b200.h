@@ -16,7 +16,10 @@
  *   - all floating point data is IEEE double; batches are design-major: q[B][E], xyz[B][n][3], ...
  *   - return value: 0 on success, a negative DFDM_E* code otherwise; dfdm_last_error() explains it
  *   - thread safety: a plan / goal program is immutable after creation and may be shared by any
- *     number of threads, streams and devices; concurrent calls must use distinct workspaces
+ *     number of threads, streams and devices; concurrent DEVICE calls must use distinct workspaces.
+ *     The *_host calls keep their device memory inside the plan, one arena per device: calls on the
+ *     same (plan, device) are serialised by a lock held for the whole call; they run on private
+ *     non-blocking streams, never on the legacy default stream
  */
 #ifndef DFDM_B200_H
 #define DFDM_B200_H
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFDM_ABI_VERSION 2
+#define DFDM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DFDM_API __attribute__((visibility("default")))
@@ -52,7 +55,7 @@ extern "C" {
 /* solver selection */
 #define DFDM_SOLVER_AUTO 0
 #define DFDM_SOLVER_DIRECT 1   /* banded LDL^T in shared memory, one CTA per design, whole eval fused */
-#define DFDM_SOLVER_PCG 2      /* Jacobi-preconditioned CG on batch-interleaved CSR */
+#define DFDM_SOLVER_PCG 2      /* CG on batch-interleaved CSR, preconditioned by aggregation multigrid (or Jacobi: DFDM_PRECOND_*) */
 
 typedef struct dfdm_plan dfdm_plan;
 typedef struct dfdm_goalprog dfdm_goalprog;
@@ -60,7 +63,9 @@ typedef struct dfdm_goalprog dfdm_goalprog;
 typedef struct dfdm_options {
     int32_t solver;          /* DFDM_SOLVER_*; AUTO picks DIRECT when the band fits shared memory */
     int32_t pcg_maxiter;     /* <= 0: default 20 * sqrt(n_free) + 2000 */
-    double pcg_rtol;         /* <= 0: default 1e-12 on ||r|| / ||b|| per design and coordinate */
+    double pcg_rtol;         /* stop test of the forward solve, ||r|| <= rtol ||b|| per design and coordinate; <= 0: the calibrated
+                                default DFDM_PCG_RTOL_DEFAULT (coordinates within 1e-9 of the direct solve with a 10x margin,
+                                tools/rtol_sweep.py, profiles/) */
     int32_t pcg_check_every; /* > 0: the host blocks on the device "all converged" counter every k iterations;
                                 <= 0 (default): the host stays two iterations ahead of the device and reads the counter of
                                 every iteration as it completes, so the device never waits for the host and at most two
@@ -75,7 +80,12 @@ typedef struct dfdm_options {
     double mg_over_w;        /* the same scaling on levels whose coarse problem is solved TWICE (the finest level and the W
                                 levels but the last): two nested corrections of scaling s combine to 1 - (1 - s)^2 <= 1, so any
                                 value below 2 keeps the preconditioner definite.  <= 0: 1.7 */
+    double pcg_rtol_adjoint; /* the same stop test for the adjoint solve K lambda = xbar (gradients within 1e-7 need fewer digits
+                                than coordinates within 1e-9); <= 0: DFDM_PCG_RTOL_ADJOINT_DEFAULT */
 } dfdm_options;
+
+#define DFDM_PCG_RTOL_DEFAULT 1e-12
+#define DFDM_PCG_RTOL_ADJOINT_DEFAULT 1e-12
 
 /* option flags */
 #define DFDM_FLAG_SPMV_MATRIX_FREE 1   /* PCG: K p straight from q over the node-edge incidence (8 E bytes per design) instead of
@@ -210,6 +220,10 @@ DFDM_API int dfdm_vjp(const dfdm_plan* plan, int32_t batch,
 /*
  * Host-buffer variants: copy inputs to the current device, evaluate, copy results back, synchronise.
  * Device memory is cached inside the library per (plan, device) and grown on demand.
+ * Large batches are pipelined: the batch is cut into chunks of designs (2 on the PCG path from 128 designs on, 4 on the
+ * direct path from 512 on); the host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 run on their
+ * own streams under the kernels of chunk k, one cudaMemcpyAsync per chunk and array.  Pinned host buffers are needed
+ * for the overlap (pageable ones still work, serialised by the driver).
  */
 DFDM_API int dfdm_forward_host(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
                       double* xyz, double* residuals, double* vectors, double* lengths, double* forces,
@@ -231,8 +245,8 @@ DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_
 #define DFDM_PROF_SPMV 0       /* k_pcg_spmv:      Ap = K p, p.Ap            algorithmic bytes 8 nnz + 48 n_free per design */
 #define DFDM_PROF_UPDATE 1     /* k_pcg_update:    r -= alpha Ap, r.r (r.z)  72 n_free (multigrid) / 80 n_free (Jacobi) per design */
 #define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: x += alpha p, p = z + beta p   108 n_free (multigrid) / 128 n_free (Jacobi) */
-#define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   8 nnz + 48 n_free + 24 n_coarse */
-#define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          8 nnz + 80 n_free + 24 n_coarse */
+#define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   4 nnz + 36 n_free + 12 n_coarse (single-precision cycle) */
+#define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          4 nnz + 52 n_free + 12 n_coarse */
 #define DFDM_PROF_MG_COARSE 5  /* all kernels below the finest level, per V-cycle */
 #define DFDM_PROF_ASSEMBLE 6   /* k_assemble: K values, 1/diag and b from q          8 E + 8 nnz + 32 n_free per design */
 #define DFDM_PROF_STATE 7      /* k_positions .. k_adjoint_rhs as one interval (loss_and_grad only): state, goals / loss,

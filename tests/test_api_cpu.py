@@ -200,7 +200,16 @@ def _gloo_worker(rank, world, port, batch, tmpdir):
     assert sb.local_slice(q).shape[0] == hi - lo
     loss, dq = sb.loss_and_grad(q)
     mean_loss, mean_dq = sb.ensemble(q)
-    torch.save({"loss": loss, "dq": dq, "mean_loss": mean_loss, "mean_dq": mean_dq}, os.path.join(tmpdir, "rank%d.pt" % rank))
+    # the other exchanges: root only; losses only (gradients stay with their designs); agreement on a per-rank verdict
+    from dfdm_b200.distributed import all_ranks_agree
+    root_loss, root_dq = ShardedBatch(evaluate, exchange="root").loss_and_grad(q)
+    assert (root_loss is None) == (rank != 0) and (root_dq is None) == (rank != 0)
+    own = ShardedBatch(evaluate, exchange="losses")
+    all_loss, own_dq = own.loss_and_grad(q)
+    assert "losses" in own.collective and own_dq.shape[0] == hi - lo and torch.equal(own_dq, 2.0 * q[lo:hi])
+    assert all_ranks_agree(True) and not all_ranks_agree(rank == 0)
+    torch.save({"loss": loss, "dq": dq, "mean_loss": mean_loss, "mean_dq": mean_dq, "root_loss": root_loss, "root_dq": root_dq,
+                "all_loss": all_loss}, os.path.join(tmpdir, "rank%d.pt" % rank))
     dist.destroy_process_group()
 
 
@@ -220,6 +229,9 @@ def test_sharded_batch_gathers_in_design_order(tmp_path, batch):
         assert torch.equal(out["dq"], 2.0 * q)
         assert torch.allclose(out["mean_loss"], (q ** 2).sum(dim=1).mean())
         assert torch.allclose(out["mean_dq"], (2.0 * q).mean(dim=0))
+        assert torch.equal(out["all_loss"], (q ** 2).sum(dim=1))
+        if rank == 0:
+            assert torch.equal(out["root_loss"], (q ** 2).sum(dim=1)) and torch.equal(out["root_dq"], 2.0 * q)
 
 
 def test_peer_gather_is_not_offered_without_nccl_ranks():

@@ -413,3 +413,68 @@ def test_matrix_free_spmv_gives_the_same_answers(mesh):
     assert _rel(outs[1]["xyz"], outs[0]["xyz"]) < TOL_X
     assert _rel(outs[1]["loss"], outs[0]["loss"]) < 1e-9
     assert _rel(outs[1]["dq"], outs[0]["dq"]) < TOL_G
+
+
+def test_grid256_matches_sparse_oracle():
+    """BASELINE configs[4] at its own size (258 x 258 nodes, 65 536 free): the multigrid-preconditioned solve with its
+    single-precision cycle and the default stop tests, against SuperLU on the same K.  Coordinates and loss within 1e-9,
+    gradients within 1e-7 (BASELINE.json); the oracle costs about a second per design."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(256)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.auto_solver == "pcg" and plan.n_free == 65536
+    ev = Evaluator(plan, loads, xyz[plan.fixed])
+    q = W.sample_q(q0, 4, seed=6, spread=0.2, relative=True)       # bench.py's own sampler and seed
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    out = ev.loss_and_grad(prog, q, outputs=STATE)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    f, a = _lib.last_pcg_iterations()
+    assert 0 < f <= 40 and 0 < a <= 40
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    for b in (0, 3):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.1)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert _rel(out["lengths"].cpu().numpy()[b], st.lengths) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+    res = out["residuals"].cpu().numpy()
+    assert np.max(np.abs(res[:, plan.free])) < 1e-9 * np.abs(res).max()
+
+
+def test_host_calls_pipeline_in_chunks_and_serialise_per_plan():
+    """dfdm_loss_and_grad_host cuts a large batch into chunks whose copies overlap the kernels; two threads sharing one plan
+    (different batch sizes, so the cached arena is regrown under them) must each get the device path's answers."""
+    import threading
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(24)
+    plan = Plan(len(fixed), edges, fixed)
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg")
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    q = W.sample_q(q0, 200, seed=2, spread=0.3, relative=True)
+    ref = ev.loss_and_grad(prog, q)
+    loss_ref, dq_ref = ref["loss"].cpu().numpy(), ref["dq"].cpu().numpy()
+    errors = []
+
+    def worker(count, rounds):
+        try:
+            for _ in range(rounds):
+                loss = np.empty(count)
+                dq = np.empty((count, len(edges)))
+                status = np.empty(count, dtype=np.int32)
+                ev.loss_and_grad_host(prog, np.ascontiguousarray(q[:count]), loss, dq, status)
+                assert np.all(status == 0)
+                assert np.allclose(loss, loss_ref[:count], rtol=1e-10, atol=0)
+                assert _rel(dq, dq_ref[:count]) < 1e-8
+        except Exception as exc:                       # noqa: BLE001 (reported to the main thread)
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(200, 3)), threading.Thread(target=worker, args=(37, 6))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

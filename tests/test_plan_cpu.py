@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert _lib.lib.dfdm_abi_version() == 2
+    assert _lib.lib.dfdm_abi_version() == 3
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
