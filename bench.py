@@ -237,7 +237,7 @@ def gpu_arm(args, rank, world, local_rank):
     plan = Plan(len(wl["is_fixed"]), wl["edges"], wl["is_fixed"])
     fixed_rows = np.nonzero(wl["is_fixed"])[0]
     ev = Evaluator(plan, wl["loads"], wl["xyz"][fixed_rows], device=device, solver=args.solver,
-                   pcg_rtol=args.pcg_rtol, pcg_rtol_adjoint=args.pcg_rtol_adjoint, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w, flags=(_lib.FLAG_SPMV_MATRIX_FREE if args.spmv_matrix_free else 0))
+                   pcg_rtol=args.pcg_rtol, pcg_rtol_adjoint=args.pcg_rtol_adjoint, pcg_check_every=args.pcg_check_every, pcg_maxiter=args.pcg_maxiter, pcg_precond=args.precond, mg_omega=args.mg_omega, mg_over=args.mg_over, mg_w_levels=args.mg_w_levels, mg_over_w=args.mg_over_w, flags=(_lib.FLAG_SPMV_MATRIX_FREE if args.spmv_matrix_free else 0) | (_lib.FLAG_MG_NO_TAIL if args.no_tail else 0))
     prog = GoalProgram(plan, *wl["program"])
     q_dev = q_host.to(device)
     E = plan.n_edges
@@ -306,7 +306,9 @@ def gpu_arm(args, rank, world, local_rank):
         count = _lib.launch_count() - launches0
         prof = _lib.profile_read()
         _lib.profile_enable(False)
-        total = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        total = sum(per_step)
+        last["ms_steps"] = per_step
         t = torch.tensor([total, float(count)], dtype=torch.float64, device=device)
         if world > 1:
             tmax = t.clone()
@@ -316,6 +318,7 @@ def gpu_arm(args, rank, world, local_rank):
         return total, count, prof
 
     ms_total, launches, _ = timed_region(False)
+    ms_steps = [round(v, 3) for v in last["ms_steps"]]
     value = batch * world * args.steps / (ms_total * 1e-3)
     prof_ms, prof_count, ms_profiled = [0.0] * 8, [0] * 8, 0.0
     if solver == "pcg" and not args.no_profile:
@@ -366,8 +369,11 @@ def gpu_arm(args, rank, world, local_rank):
             "e2e": {"value": batch * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world,
                     "api": "dfdm_loss_and_grad_host (pinned host buffers; the batch is cut into chunks whose copies run under the kernels of the neighbouring chunk)"},
-            "gpu_launches": launches}
-    if solver == "pcg" and sum(prof_count) > 0:
+            "gpu_launches": launches, "ms_steps": ms_steps}
+    if solver == "pcg" and sum(prof_count) == 0:
+        line["roofline"] = {"bound": "hbm", "kernel": "whole step (per-kernel table skipped: --no-profile)", "achieved": None, "peak": peak, "unit": "GB/s",
+                            "frac": None, "traffic": None, "peak_source": peak_src}
+    elif solver == "pcg":
         nc = plan.info.get("mg_n_coarse", 0)
         is_mg = plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi"
         # update: r in/out, Ap (+ 1/diag for Jacobi); direction: p in/out, x in/out, z (float) or r + 1/diag
@@ -567,6 +573,7 @@ def main():
     ap.add_argument("--mg-over", type=float, default=0.0)
     ap.add_argument("--mg-over-w", type=float, default=0.0)
     ap.add_argument("--spmv-matrix-free", action="store_true", help="K p from q over the incidence lists instead of the stored CSR values")
+    ap.add_argument("--no-tail", action="store_true", help="coarse multigrid levels on the launch-per-level path instead of the tail kernel")
     ap.add_argument("--mg-w-levels", type=int, default=0, help="coarse levels visited twice per cycle (0: default 3, -1: V-cycle)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")

@@ -69,7 +69,34 @@ static int upload_mg(const Plan& P, int device, MgDev& out) {
     M.n_levels = (int)P.mg.size();
     for (int l = 0; l < M.n_levels; ++l) {
         const MgLevel& L = P.mg[l];
-        const std::vector<int32_t>* arrays[] = {&L.agg, &L.mem_ptr, &L.mem_idx, &L.rowptr, &L.ell_col, &L.diagslot, &L.gal_ptr, &L.gal_src};
+        // sliced ELL tables of this level's operator (k_mg_tail): slices of 32 rows, each as wide as its widest row
+        const int slices = (L.n + 31) / 32;
+        std::vector<int32_t> tl_off(slices + 1, 0), tl_col, tl_src, tl_agg;
+        for (int sl = 0; sl < slices; ++sl) {
+            int wmax = 0;
+            for (int f = sl * 32; f < std::min(L.n, sl * 32 + 32); ++f) wmax = std::max(wmax, L.rowptr[f + 1] - L.rowptr[f]);
+            tl_off[sl + 1] = tl_off[sl] + wmax;
+        }
+        const int64_t ent = (int64_t)tl_off[slices] * 32;
+        tl_col.assign((size_t)ent, 0);
+        tl_src.assign((size_t)ent, -1);
+        const bool has_next = l + 1 < M.n_levels;
+        if (has_next) tl_agg.assign((size_t)ent, 0);
+        for (int sl = 0; sl < slices; ++sl)
+            for (int u = 0; u < tl_off[sl + 1] - tl_off[sl]; ++u)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int f = sl * 32 + lane;
+                    const size_t at = ((size_t)tl_off[sl] + u) * 32 + lane;
+                    int col = std::min(f, L.n - 1);
+                    if (f < L.n && L.rowptr[f] + u < L.rowptr[f + 1]) {
+                        col = L.colidx[L.rowptr[f] + u];
+                        tl_src[at] = L.rowptr[f] + u;
+                    }
+                    tl_col[at] = col;
+                    if (has_next) tl_agg[at] = P.mg[l + 1].agg[col];
+                }
+        const std::vector<int32_t>* arrays[] = {&L.agg, &L.mem_ptr, &L.mem_idx, &L.rowptr, &L.ell_col, &L.diagslot, &L.gal_ptr, &L.gal_src,
+                                                &tl_off, &tl_col, &tl_src, &tl_agg};
         constexpr int NA = sizeof(arrays) / sizeof(arrays[0]);
         int64_t offs[NA], total = 0;
         for (int k = 0; k < NA; ++k) {
@@ -86,6 +113,8 @@ static int upload_mg(const Plan& P, int device, MgDev& out) {
         D.n_fine = L.n_fine; D.n = L.n; D.nnz = L.nnz; D.ell_w = L.ell_w;
         D.agg = at(0); D.mem_ptr = at(1); D.mem_idx = at(2); D.rowptr = at(3); D.ell_col = at(4); D.diagslot = at(5);
         D.gal_ptr = at(6); D.gal_src = at(7);
+        D.tl_slices = slices; D.tl_ent = ent; D.tl_off = at(8); D.tl_col = at(9); D.tl_src = at(10);
+        D.tl_agg = has_next ? at(11) : nullptr;
         P.dev_block[1000 * (l + 1) + device] = block;     // freed with the plan (key unique per level and device)
     }
     P.mg_dev[device] = M;

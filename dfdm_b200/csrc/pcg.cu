@@ -15,6 +15,7 @@
 // Reference being replaced: np.linalg.solve in src/dfdm/equilibrium/model.py:55 (for networks whose
 // banded factor does not fit shared memory) plus the assembly of model.py:50-54 and the
 // post-processing of model.py:21-34, batched.
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -1132,6 +1133,328 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The coarse levels from level `tail` down in ONE launch per visit: k_mg_tail.
+//
+// Designs never couple, so the whole sub-cycle below a level (W revisits included) can be walked by ONE CTA per design
+// pair with nothing but block barriers between its stages - no kernel boundaries, no cluster or grid barriers.  What that
+// needs is a layout in which one pair's data is contiguous: the operators of the tail levels are repacked once per
+// evaluation (k_pack_pairs) from the batch-interleaved arrays into PAIR-MAJOR sliced-ELL tables (float2 = the two designs
+// of the pair; rows in slices of 32, padded per slice, so a warp reads 256 consecutive bytes per matrix position).
+// Every vector that is GATHERED through the column indices lives in shared memory (a gather of 8-byte words from
+// global memory costs one L1 tag look-up per lane; measured, that - not bandwidth or latency - bounded the first version
+// of this kernel): right-hand sides, solutions and W-cycle residuals of the levels below the top one, and ONE staging
+// buffer for the top level that holds, in turn, its right-hand side, its first solution and its residual.  Vectors
+// that a thread reads only at its own row (t, 1/diag, the top level's own-row copies) are pair-major global arrays,
+// read and written coalesced.  The right-hand side comes in and the solution goes out in the interleaved layout of the
+// levels above.  Arithmetic and summation order are those of k_mg_down / k_mg_up / k_mg_resid and the dense coarsest
+// product, so the preconditioner (and the iteration counts) are unchanged.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailMax = 8;              // levels inside the tail kernel, the coarsest (dense inverse) included
+constexpr int kTailThreads = 1024;
+constexpr int kTailRowsMax = 8192;       // largest level the workspace provides pair-major arrays for
+#ifndef DFDM_TAIL_U
+#define DFDM_TAIL_U 5
+#endif
+constexpr int kTailU = DFDM_TAIL_U;      // matrix positions in flight per thread
+
+struct TailLevel {
+    int n, nc;                           // rows of this level / of the next coarser one
+    int twice;                           // W level: two cycles per visit
+    float over;                          // scaling of this level's coarse-grid correction
+    const int32_t *off, *col, *aggc, *agg, *mem_ptr;
+    const float2* vals;                  // [pairs][ent] K, sliced ELL, zero where padded
+    const float2* vals_s;                // [pairs][ent] K D^-1
+    const float2* d;                     // [pairs][n]   1 / diag
+    int64_t ent;
+    float2* t;                           // [pairs][3 n] global, own-row only
+    // gathered vectors: offsets (float2) into shared memory; below the top level b, z and r2 each have their own,
+    // on the top level they share ONE staging buffer (sb == sz == sr) and the own-row copies live in gb / gz / gr
+    int sb, sz, sr;
+    float2 *gb, *gz, *gr;                // [pairs][3 n] global own-row copies (top level only; null below)
+};
+struct TailArgs {
+    int count;                           // levels, the coarsest last
+    TailLevel L[kTailMax];
+    const float2* inv;                   // [pairs][n * n], (j n + i)
+    float omega;
+    long long* trace;                    // tuning only (DFDM_TAIL_TRACE): CTA 0 logs (tag, clock) after every stage
+};
+#define TAIL_MARK(tag)                                                                   \
+    do {                                                                                 \
+        if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < 1000) {             \
+            a.trace[2 + 2 * tr_n] = (tag);                                               \
+            a.trace[3 + 2 * tr_n] = clock64();                                           \
+            ++tr_n;                                                                      \
+            a.trace[0] = tr_n;                                                           \
+        }                                                                                \
+    } while (0)
+
+// src[(map ? map[i] : i)][B] (two neighbouring designs = one float2) -> dst[pair][count]; zero where map[i] < 0
+__global__ void __launch_bounds__(256) k_pack_pairs(const float* __restrict__ src, const int32_t* __restrict__ map, int64_t count, int B,
+                                                    float2* __restrict__ dst) {
+    __shared__ float2 tile[32][33];
+    const int pairs = B >> 1;
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int p0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t i = i0 + j;
+        const int p = p0 + threadIdx.x;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i < count && p < pairs) {
+            const int64_t sidx = map ? (int64_t)map[i] : i;
+            if (sidx >= 0) v = reinterpret_cast<const float2*>(src + sidx * B)[p];
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int p = p0 + j;
+        const int64_t i = i0 + threadIdx.x;
+        if (i < count && p < pairs) dst[(size_t)p * count + i] = tile[threadIdx.x][j];
+    }
+}
+
+// acc[c] += sum_u vals(f, u) * x[c][col(f, u)] over row f of the sliced table; x is in SHARED memory
+__device__ __forceinline__ void tail_row(const int32_t* __restrict__ off, const int32_t* __restrict__ coltab, const float2* __restrict__ vals,
+                                         const float2* x, int nx, int f, float2 (&acc)[3]) {
+    constexpr int U = kTailU;
+    const int sl = f >> 5, lane = f & 31;
+    const int o0 = off[sl], w = off[sl + 1] - o0;
+    for (int u0 = 0; u0 < w; u0 += U) {
+        int col[U];
+        float2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = (o0 + min(u0 + u, w - 1)) * 32 + lane;
+            col[u] = __ldg(coltab + idx);
+            v[u] = __ldg(vals + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u0 + u >= w) v[u] = make_float2(0.0f, 0.0f);
+            const float2 x0 = x[col[u]], x1 = x[nx + col[u]], x2 = x[2 * nx + col[u]];
+            acc[0].x += v[u].x * x0.x; acc[0].y += v[u].y * x0.y;
+            acc[1].x += v[u].x * x1.x; acc[1].y += v[u].y * x1.y;
+            acc[2].x += v[u].x * x2.x; acc[2].y += v[u].y * x2.y;
+        }
+    }
+}
+
+// down pass of one level: t = (K D^-1) rhs; the smoothed residual rhs - w t is parked, then summed over every aggregate.
+// rhs_g: gather source (shared); rhs_o: the same vector for own-row reads; bc: right-hand side of the next level (shared)
+__device__ void tail_down(const TailLevel& L, const float2* vals_s, const float2* rhs_g, const float2* rhs_o, float2* t, float2* park,
+                          float2* bc, float omega) {
+    const int n = L.n, nc = L.nc;
+    for (int f = threadIdx.x; f < n; f += kTailThreads) {
+        float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        tail_row(L.off, L.col, vals_s, rhs_g, n, f, acc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 b = rhs_o[c * n + f];
+            t[c * n + f] = acc[c];
+            park[c * n + f] = make_float2(b.x - omega * acc[c].x, b.y - omega * acc[c].y);
+        }
+    }
+    __syncthreads();
+    for (int I = threadIdx.x; I < nc; I += kTailThreads) {
+        const int m0 = L.mem_ptr[I], m1 = L.mem_ptr[I + 1];
+        float2 rc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        for (int m = m0; m < m1; ++m)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 r1 = park[c * n + m];
+                rc[c].x += r1.x;
+                rc[c].y += r1.y;
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bc[c * nc + I] = rc[c];
+    }
+    __syncthreads();
+}
+
+// up pass: out (+)= x' + w D^-1 (rhs - K x'), x' = w D^-1 rhs + s P e.  e: solution of the next level (shared).
+// The result goes to out (own rows; prev is read there when accumulating), to out2 (nullable: the staging buffer) and,
+// on the way out of the kernel, to the interleaved array of the level above (out_il, nullable).
+__device__ void tail_up(const TailLevel& L, const float2* vals, const float2* d, const float2* rhs_o, const float2* t, const float2* e,
+                        float2* out, float2* out2, float2* out_il, size_t il_stride, bool accumulate, float omega) {
+    const int n = L.n, nc = L.nc;
+    const float over = L.over;
+    for (int f = threadIdx.x; f < n; f += kTailThreads) {
+        float2 sacc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        tail_row(L.off, L.aggc, vals, e, nc, f, sacc);
+        const float2 wd = d[f];
+        const int I = L.agg[f];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 b = rhs_o[c * n + f], tc = t[c * n + f], ec = e[c * nc + I];
+            float2 z;
+            {
+                const float w1 = omega * wd.x;
+                const float xn = w1 * b.x + over * ec.x;
+                z.x = xn + w1 * (b.x - omega * tc.x - over * sacc[c].x);
+            }
+            {
+                const float w1 = omega * wd.y;
+                const float xn = w1 * b.y + over * ec.y;
+                z.y = xn + w1 * (b.y - omega * tc.y - over * sacc[c].y);
+            }
+            if (accumulate) {
+                const float2 prev = out[c * n + f];
+                z.x += prev.x;
+                z.y += prev.y;
+            }
+            if (out_il) out_il[(size_t)(f * 3 + c) * il_stride] = z;
+            else out[c * n + f] = z;
+            if (out2) out2[c * n + f] = z;
+        }
+    }
+    __syncthreads();
+}
+
+// r2 = rhs - K x  (x gathered from shared memory)
+__device__ void tail_resid(const TailLevel& L, const float2* vals, const float2* rhs_o, const float2* x_g, float2* r2) {
+    const int n = L.n;
+    for (int f = threadIdx.x; f < n; f += kTailThreads) {
+        float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        tail_row(L.off, L.col, vals, x_g, n, f, acc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 b = rhs_o[c * n + f];
+            r2[c * n + f] = make_float2(b.x - acc[c].x, b.y - acc[c].y);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, const float* __restrict__ rhs_il, float* __restrict__ out_il,
+                                                            const int32_t* __restrict__ n_active) {
+    pdl_wait();
+    if (__ldcg(&n_active[1]) == 0) return;
+    extern __shared__ float2 tsm[];
+    const int tid = threadIdx.x;
+    const int pairs = B >> 1;
+    const int last = a.count - 1;
+    const float omega = a.omega;
+    const size_t il_stride = (size_t)B / 2;                 // float2 elements between consecutive (row, coordinate) entries
+    int tr_n = 0;
+    TAIL_MARK(0);
+    for (int pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        const int n0 = a.L[0].n;
+        float2* const S = tsm + a.L[0].sb;                  // staging buffer of the top level
+        float2* const gb0 = a.L[0].gb + (size_t)pair * 3 * n0;
+        float2* const gz0 = a.L[0].gz + (size_t)pair * 3 * n0;
+        float2* const gr0 = a.L[0].gr + (size_t)pair * 3 * n0;
+        {   // right-hand side of the top level, from the interleaved layout of the level above
+            const float2* src = reinterpret_cast<const float2*>(rhs_il) + pair;
+            constexpr int UI = 4;
+            for (int i0 = tid; i0 < 3 * n0; i0 += UI * kTailThreads) {
+                float2 v[UI];
+#pragma unroll
+                for (int u = 0; u < UI; ++u) {
+                    const int idx = i0 + u * kTailThreads;
+                    const int c = idx / n0, f = idx - c * n0;
+                    v[u] = idx < 3 * n0 ? __ldcg(src + (size_t)(f * 3 + c) * il_stride) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < UI; ++u) {
+                    const int idx = i0 + u * kTailThreads;
+                    if (idx < 3 * n0) {
+                        S[idx] = v[u];
+                        gb0[idx] = v[u];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        TAIL_MARK(1);
+        // ---- the cycle: an explicit walk instead of recursion (every thread takes the same path) -----------------
+        int phase[kTailMax];
+#pragma unroll
+        for (int k = 0; k < kTailMax; ++k) phase[k] = 0;
+        int k = 0;
+        while (true) {
+            const TailLevel& L = a.L[k];
+            if (k == last) {                               // dense product with the explicit inverse
+                const int nn = L.n;
+                const float2* inv = a.inv + (size_t)pair * nn * nn;
+                const float2* b = tsm + L.sb;
+                float2* e = tsm + L.sz;
+                for (int idx = tid; idx < 3 * nn; idx += kTailThreads) {
+                    const int c = idx / nn, i = idx - c * nn;
+                    float2 s = make_float2(0.f, 0.f);
+                    constexpr int UC = 10;
+                    for (int j0 = 0; j0 < nn; j0 += UC) {
+                        float2 wv[UC];
+#pragma unroll
+                        for (int u = 0; u < UC; ++u) wv[u] = j0 + u < nn ? __ldg(inv + (size_t)(j0 + u) * nn + i) : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < UC; ++u) {
+                            const float2 x = b[c * nn + min(j0 + u, nn - 1)];
+                            s.x += wv[u].x * x.x;
+                            s.y += wv[u].y * x.y;
+                        }
+                    }
+                    e[idx] = s;
+                }
+                __syncthreads();
+                TAIL_MARK(900 + k);
+                if (k == 0) break;
+                --k;
+                continue;
+            }
+            const int n = L.n;
+            const bool top = k == 0;
+            const float2* vals = L.vals + (size_t)pair * L.ent;
+            const float2* vals_s = L.vals_s + (size_t)pair * L.ent;
+            const float2* d = L.d + (size_t)pair * n;
+            float2* t = L.t + (size_t)pair * 3 * n;
+            float2* sb = tsm + L.sb;
+            float2* sz = tsm + L.sz;
+            float2* sr = tsm + L.sr;
+            float2* bnext = tsm + a.L[k + 1].sb;
+            const float2* znext = tsm + a.L[k + 1].sz;
+            if (phase[k] == 0) {
+                // first cycle: residuals are parked where the solution will go
+                tail_down(L, vals_s, sb, top ? gb0 : sb, t, top ? gz0 : sz, bnext, omega);
+                TAIL_MARK(100 + k);
+                phase[k] = 1;
+                ++k;
+                phase[k] = 0;
+            } else if (phase[k] == 1) {
+                const bool final_pass = top && !L.twice;
+                tail_up(L, vals, d, top ? gb0 : sb, t, znext, top ? gz0 : sz, (top && L.twice) ? S : nullptr,
+                        final_pass ? reinterpret_cast<float2*>(out_il) + pair : nullptr, il_stride, false, omega);
+                TAIL_MARK(200 + k);
+                if (L.twice) {                             // second cycle on the residual of the first
+                    tail_resid(L, vals, top ? gb0 : sb, top ? S : sz, top ? gr0 : sr);
+                    TAIL_MARK(300 + k);
+                    if (top) {                             // the staging buffer now takes the residual (it was being gathered until here)
+                        for (int idx = tid; idx < 3 * n; idx += kTailThreads) S[idx] = gr0[idx];
+                        __syncthreads();
+                    }
+                    // the first right-hand side is dead: its storage parks the residuals of this pass
+                    tail_down(L, vals_s, top ? S : sr, top ? gr0 : sr, t, top ? gb0 : sb, bnext, omega);
+                    TAIL_MARK(400 + k);
+                    phase[k] = 2;
+                    ++k;
+                    phase[k] = 0;
+                } else {
+                    if (top) break;
+                    --k;
+                }
+            } else {
+                tail_up(L, vals, d, top ? gr0 : sr, t, znext, top ? gz0 : sz, nullptr,
+                        top ? reinterpret_cast<float2*>(out_il) + pair : nullptr, il_stride, true, omega);
+                TAIL_MARK(500 + k);
+                if (top) break;
+                --k;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // W-cycle helper on a coarse level: r2 = rhs - A x
 template <int V>
 __global__ void __launch_bounds__(kThreads, 4) k_mg_resid(MgMat A, LaneCfg cfg, int B, const mgf* __restrict__ rhs,
@@ -1554,6 +1877,17 @@ struct MgBuffers {
     mgf* r2[kMaxMgLevels + 1] = {nullptr};             // W-cycle: residual after the first visit
     mgf* inv = nullptr;
     mgf* tmp = nullptr;
+    // pair-major copies for the tail kernel (levels tail_first .. n_levels; nullptr above)
+    int tail_first = 0;                                // first level the workspace holds pair-major arrays for (0: none)
+    int tail = 0;                                      // level the tail kernel takes over at in this evaluation (0: not used)
+    float2* pv[kMaxMgLevels + 1] = {nullptr};          // operator, sliced ELL
+    float2* pvs[kMaxMgLevels + 1] = {nullptr};         // operator with scaled columns (K D^-1), sliced ELL
+    float2* pd[kMaxMgLevels + 1] = {nullptr};          // 1 / diag
+    float2* pb[kMaxMgLevels + 1] = {nullptr};
+    float2* pt[kMaxMgLevels + 1] = {nullptr};
+    float2* pz[kMaxMgLevels + 1] = {nullptr};
+    float2* pr[kMaxMgLevels + 1] = {nullptr};
+    float2* pinv = nullptr;
 };
 
 struct PcgBuffers {
@@ -1568,7 +1902,7 @@ struct PcgBuffers {
 };
 
 static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int64_t B, int nslabs_max,
-                  int nchunks_max, PcgBuffers& w, int mg_levels, const int* mg_n, const int* mg_nnz) {
+                  int nchunks_max, PcgBuffers& w, int mg_levels, const int* mg_n, const int* mg_nnz, const int64_t* mg_ent) {
     w.mg.n_levels = mg_levels;
     if (mg_levels > 0) {
         w.mg.vals[0] = bump.take<mgf>(nnz * B);
@@ -1590,6 +1924,24 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
             w.mg.inv = bump.take<mgf>(nc * nc * B);
         } else {
             w.mg.tmp = bump.take<mgf>(nc * 3 * B);
+        }
+        if (B % 2 == 0 && nc <= kCoarsestDense) {       // pair-major arrays of the tail kernel (counting mode: pointers are null)
+            const int64_t pairs = B / 2;
+            for (int l = 1; l <= mg_levels; ++l) {
+                if (mg_n[l - 1] > kTailRowsMax || mg_levels - l + 1 > kTailMax) continue;
+                if (!w.mg.tail_first) w.mg.tail_first = l;
+                const int64_t nl = mg_n[l - 1];
+                if (l < mg_levels) {
+                    w.mg.pv[l] = bump.take<float2>(mg_ent[l - 1] * pairs);
+                    w.mg.pvs[l] = bump.take<float2>(mg_ent[l - 1] * pairs);
+                    w.mg.pd[l] = bump.take<float2>(nl * pairs);
+                    w.mg.pt[l] = bump.take<float2>(nl * 3 * pairs);
+                    w.mg.pr[l] = bump.take<float2>(nl * 3 * pairs);
+                }
+                w.mg.pb[l] = bump.take<float2>(nl * 3 * pairs);
+                w.mg.pz[l] = bump.take<float2>(nl * 3 * pairs);
+            }
+            if (w.mg.tail_first) w.mg.pinv = bump.take<float2>(nc * nc * pairs);
         }
     }
     w.qT = bump.take<double>(E * B);
@@ -1636,8 +1988,13 @@ int64_t pcg_workspace(const Plan& P, int B) {
     Bump bump(nullptr);
     PcgBuffers w{};
     int mn[kMaxMgLevels], mz[kMaxMgLevels];
-    for (size_t l = 0; l < P.mg.size(); ++l) { mn[l] = P.mg[l].n; mz[l] = P.mg[l].nnz; }
-    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, (int)P.mg.size(), mn, mz);
+    int64_t me[kMaxMgLevels];
+    for (size_t l = 0; l < P.mg.size(); ++l) {
+        mn[l] = P.mg[l].n;
+        mz[l] = P.mg[l].nnz;
+        me[l] = tail_entries(P.mg[l].rowptr, P.mg[l].n);
+    }
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, (int)P.mg.size(), mn, mz, me);
     return bump.off;
 }
 
@@ -1710,6 +2067,51 @@ static MgMat mg_mat(const PlanDev& P, const MgDev& M, const PcgBuffers& w, int l
     return A;
 }
 
+static int resolve_w_levels(const dfdm_options& opt, int n_levels) {
+    // cycle shape: coarse levels 1 .. w_levels are visited twice (W-cycle); deeper levels once.  Plain aggregation gains
+    // most from revisiting the first coarse levels; the default is 3.
+    int w_levels = opt.mg_w_levels < 0 ? 0 : (opt.mg_w_levels > 0 ? opt.mg_w_levels : 3);
+    return std::min(w_levels, std::max(0, n_levels - 1));
+}
+
+// shared memory (float2 elements) the tail kernel needs when it takes over at level l0: one staging buffer for the top
+// level, right-hand side and solution for every level below it, a residual for the W levels among those
+static int64_t tail_smem_elems(const MgDev& M, int l0, int w_levels) {
+    int64_t total = 3 * (int64_t)M.lv[l0 - 1].n;
+    for (int l = l0 + 1; l <= M.n_levels; ++l) {
+        const int64_t n = M.lv[l - 1].n;
+        total += 2 * ((3 * n + 1) & ~(int64_t)1);
+        if (l < M.n_levels && l <= w_levels) total += (3 * n + 1) & ~(int64_t)1;
+    }
+    return total;
+}
+
+// Level at which the tail kernel takes over: the first coarse level with at most DFDM_MG_TAIL rows (default 6144; 0: off)
+// whose gathered vectors fit shared memory, provided the workspace holds the pair-major arrays (even batch, dense
+// coarsest inverse).
+static int choose_tail(const MgDev& M, const PcgBuffers& w, const dfdm_options& opt) {
+    if (opt.flags & DFDM_FLAG_MG_NO_TAIL) return 0;
+    static const int rows = [] {
+        const char* v = std::getenv("DFDM_MG_TAIL");
+        int r = v ? std::atoi(v) : 6144;
+        return r < 0 ? 0 : (r > kTailRowsMax ? kTailRowsMax : r);
+    }();
+    if (!w.mg.tail_first || rows == 0) return 0;
+    int dev = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    const int w_levels = resolve_w_levels(opt, M.n_levels);
+    for (int l = w.mg.tail_first; l < M.n_levels; ++l)          // at least two levels: l and the coarsest
+        if (M.lv[l - 1].n <= rows && tail_smem_elems(M, l, w_levels) * (int64_t)sizeof(float2) <= smem_max) return l;
+    return 0;
+}
+
+static int pack_pairs(const float* src, const int32_t* map, int64_t count, int B, float2* dst, cudaStream_t st) {
+    dim3 grid((unsigned)((count + 31) / 32), (unsigned)((B / 2 + 31) / 32)), block(32, 8);
+    k_pack_pairs<<<grid, block, 0, st>>>(src, map, count, B, dst);
+    DFDM_LAUNCH_OK("k_pack_pairs");
+    return DFDM_OK;
+}
+
 // numerical set-up of the hierarchy for the assembled K of this evaluation (once per evaluation)
 static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B, PcgBuffers& w, cudaStream_t st) {
     const int nl = M.n_levels;
@@ -1751,6 +2153,19 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
         k_mg_coarsest_invert<<<B, 256, smem, st>>>(C.n, C.rowptr, C.ell_col, C.ell_w, B, w.mg.vals[nl], w.mg.inv);
         DFDM_LAUNCH_OK("k_mg_coarsest_invert");
     }
+    if (w.mg.tail > 0) {                                  // pair-major copies of the tail levels' operators
+        for (int l = w.mg.tail; l < nl; ++l) {
+            const MgLevelDev& A = M.lv[l - 1];
+            int rc = pack_pairs(w.mg.vals[l], A.tl_src, A.tl_ent, B, w.mg.pv[l], st);
+            if (rc) return rc;
+            rc = pack_pairs(w.mg.vals_s[l], A.tl_src, A.tl_ent, B, w.mg.pvs[l], st);
+            if (rc) return rc;
+            rc = pack_pairs(w.mg.dinv[l], nullptr, A.n, B, w.mg.pd[l], st);
+            if (rc) return rc;
+        }
+        int rc = pack_pairs(w.mg.inv, nullptr, (int64_t)C.n * C.n, B, w.mg.pinv, st);
+        if (rc) return rc;
+    }
     return DFDM_OK;
 }
 
@@ -1778,6 +2193,7 @@ struct MgCtx {
     LaneCfg vbase;
     int w_levels;          // coarse levels 1 .. w_levels are visited twice per visit of their parent (W-cycle)
     int bottom;            // first level handled by the single-launch bottom kernel (0: none)
+    int tail;              // first level handled by the one-CTA-per-pair tail kernel (0: none); takes precedence
 };
 
 // out = M_l rhs on coarse level l (1 <= l <= n_levels): exact on the coarsest level, one (V) or two (W) cycles above it
@@ -1881,11 +2297,99 @@ static int mg_bottom(const MgCtx& c, const mgf* rhs, mgf* out, int acc) {
     return DFDM_OK;
 }
 
+// levels c.tail .. coarsest, W revisits included, in one launch of one CTA per design pair: out = M_l rhs
+static int mg_tail(const MgCtx& c, const mgf* rhs, mgf* out) {
+    const MgDev& M = *c.M;
+    PcgBuffers& w = *c.w;
+    const int nl = M.n_levels, l0 = c.tail;
+    int dev = 0, sms = 148;
+    DFDM_CUDA_OK(cudaGetDevice(&dev));
+    DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TailArgs a{};
+    a.count = nl - l0 + 1;
+    a.omega = c.mp.omega;
+    a.inv = w.mg.pinv;
+    static long long* trace_buf = [] {
+        long long* p = nullptr;
+        if (std::getenv("DFDM_TAIL_TRACE")) cudaMallocManaged(&p, sizeof(long long) * 2048);
+        return p;
+    }();
+    a.trace = trace_buf;
+    int64_t cursor = 0;                                        // float2 elements of shared memory
+    auto take = [&](int64_t elems) {
+        const int at = (int)cursor;
+        cursor += (elems + 1) & ~(int64_t)1;
+        return at;
+    };
+    for (int k = 0; k < a.count; ++k) {
+        const int l = l0 + k;
+        TailLevel& T = a.L[k];
+        T.n = M.lv[l - 1].n;
+        if (l < nl) {
+            const MgLevelDev& A = M.lv[l - 1];
+            const MgLevelDev& G = M.lv[l];
+            T.nc = G.n;
+            T.twice = l <= c.w_levels ? 1 : 0;
+            T.over = l < c.w_levels ? c.mp.over : c.mp_single.over;
+            T.off = A.tl_off; T.col = A.tl_col; T.aggc = A.tl_agg; T.agg = G.agg; T.mem_ptr = G.mem_ptr;
+            T.vals = w.mg.pv[l];
+            T.vals_s = w.mg.pvs[l];
+            T.d = w.mg.pd[l];
+            T.ent = A.tl_ent;
+            T.t = w.mg.pt[l];
+        }
+        if (k == 0) {
+            T.sb = T.sz = T.sr = take(3 * (int64_t)T.n);       // one staging buffer
+            T.gb = w.mg.pb[l]; T.gz = w.mg.pz[l]; T.gr = w.mg.pr[l];
+        } else {
+            T.sb = take(3 * (int64_t)T.n);
+            T.sz = take(3 * (int64_t)T.n);
+            T.sr = (l < nl && T.twice) ? take(3 * (int64_t)T.n) : T.sb;
+        }
+    }
+    const size_t smem = (size_t)cursor * sizeof(float2);
+    if (smem > 48 * 1024) {
+        static std::mutex mu;
+        static std::map<int, size_t> configured;
+        std::lock_guard<std::mutex> lock(mu);
+        if (configured[dev] < smem) {
+            DFDM_CUDA_OK(cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = smem;
+        }
+    }
+    const int pairs = c.B / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::min(pairs, sms));
+    cfg.blockDim = dim3(kTailThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DFDM_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mg_tail, a, c.B, (const float*)rhs, (float*)out, (const int32_t*)(w.S.n_active + w.S.par)));
+    DFDM_LAUNCH_OK("k_mg_tail");
+    if (trace_buf) {                                           // tuning only: one synchronous dump per launch
+        cudaStreamSynchronize(c.st);
+        static int dumped = 0;
+        if (dumped++ == 40) {
+            long long n = trace_buf[0], t0 = trace_buf[3];
+            for (long long i = 0; i < n; ++i)
+                fprintf(stderr, "tail-trace %3lld tag %4lld  at %9lld  (+%lld)\n", i, trace_buf[2 + 2 * i], trace_buf[3 + 2 * i] - t0,
+                        i ? trace_buf[3 + 2 * i] - trace_buf[1 + 2 * i] : 0LL);
+        }
+        trace_buf[0] = 0;
+    }
+    return DFDM_OK;
+}
+
 template <int V>
 static int mg_solve_level(const MgCtx& c, int l, const mgf* rhs, mgf* out) {
     const MgDev& M = *c.M;
     PcgBuffers& w = *c.w;
     const int nl = M.n_levels;
+    if (V == 2 && c.tail > 0 && l == c.tail) return mg_tail(c, rhs, out);
     if (V == 2 && c.bottom > 0 && l == c.bottom) return mg_bottom(c, rhs, out, 0);
     if (l == nl) {
         const MgLevelDev& C = M.lv[nl - 1];
@@ -1928,7 +2432,9 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     }
     MgParams mpw = mp;
     mpw.over = over_w;
-    MgCtx c{&P, &M, &w, B, st, mpw, mp, vec_base(B, V), w_levels, bottom};
+    const int tail = V == 2 ? w.mg.tail : 0;
+    if (tail > 0 && bottom >= tail) bottom = 0;
+    MgCtx c{&P, &M, &w, B, st, mpw, mp, vec_base(B, V), w_levels, bottom, tail};
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     MgMat A = mg_mat(P, M, w, 0);
     LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
@@ -1988,8 +2494,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     // cycle shape: coarse levels 1 .. w_levels are visited twice (W-cycle); deeper levels once.  Plain aggregation gains
     // most from revisiting the first coarse levels; the tiny ones below are latency bound (8 visits of the cluster kernel
     // per cycle is where a fourth W level stops paying), so the default is 3.
-    int w_levels = opt.mg_w_levels < 0 ? 0 : (opt.mg_w_levels > 0 ? opt.mg_w_levels : 3);
-    if (mg) w_levels = std::min(w_levels, std::max(0, M->n_levels - 1));
+    const int w_levels = mg ? resolve_w_levels(opt, M->n_levels) : 0;
     MgParams mp{(float)(opt.mg_omega > 0 ? opt.mg_omega : kMgOmegaDefault),
                 (float)(opt.mg_over > 0 ? opt.mg_over : (w_levels > 0 ? kMgOverW : kMgOverDefault))};
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
@@ -2134,8 +2639,10 @@ int run_pcg(Eval& ev) {
     PcgBuffers w{};
     const bool use_mg = ev.M.n_levels > 0 && ev.opt.pcg_precond != DFDM_PRECOND_JACOBI;
     int mn[kMaxMgLevels], mz[kMaxMgLevels];
-    for (int l = 0; l < ev.M.n_levels; ++l) { mn[l] = ev.M.lv[l].n; mz[l] = ev.M.lv[l].nnz; }
-    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, ev.M.n_levels, mn, mz);
+    int64_t me[kMaxMgLevels];
+    for (int l = 0; l < ev.M.n_levels; ++l) { mn[l] = ev.M.lv[l].n; mz[l] = ev.M.lv[l].nnz; me[l] = ev.M.lv[l].tl_ent; }
+    carve(bump, P.n, P.E, P.nf, P.nnz, B, kMaxSlabs, B, w, ev.M.n_levels, mn, mz, me);
+    w.mg.tail = use_mg ? choose_tail(ev.M, w, ev.opt) : 0;
     if (bump.off > ev.ws_bytes) {
         set_error("workspace too small for the PCG path: need " + std::to_string(bump.off) + " bytes");
         return DFDM_ENOMEM;

@@ -63,6 +63,15 @@ struct MgLevelDev {
     const int32_t* diagslot = nullptr;   // [n]
     const int32_t* gal_ptr = nullptr;    // [nnz+1]  coarse slot -> fine slots (Galerkin sum)
     const int32_t* gal_src = nullptr;    // [nnz_fine]
+    // the same operator as a SLICED ELL table for the one-CTA-per-design-pair tail kernel (pcg.cu k_mg_tail): rows in
+    // slices of 32, every slice padded to its own widest row; entry (slice s, position u, lane) lives at
+    // (tl_off[s] + u) * 32 + lane, so the 32 rows of a slice read consecutive words
+    int tl_slices = 0;
+    int64_t tl_ent = 0;                  // 32 * sum of the slice widths
+    const int32_t* tl_off = nullptr;     // [tl_slices + 1] prefix sums of the slice widths
+    const int32_t* tl_col = nullptr;     // [tl_ent] column (the row itself where padded)
+    const int32_t* tl_src = nullptr;     // [tl_ent] CSR slot of the entry, -1 where padded
+    const int32_t* tl_agg = nullptr;     // [tl_ent] aggregate (row of the next coarser level) of that column; null on the last level
 };
 constexpr int kMaxMgLevels = 12;
 struct MgDev {
@@ -74,6 +83,17 @@ struct MgLevel {
     int n_fine = 0, n = 0, nnz = 0, ell_w = 0;
     std::vector<int32_t> agg, mem_ptr, mem_idx, rowptr, colidx, ell_col, diagslot, gal_ptr, gal_src;
 };
+
+// entries of a level's operator in the sliced ELL layout of the tail kernel (slices of 32 rows padded to their widest row)
+inline int64_t tail_entries(const std::vector<int32_t>& rowptr, int n) {
+    int64_t total = 0;
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        int wmax = 0;
+        for (int f = s0; f < n && f < s0 + 32; ++f) wmax = wmax > rowptr[f + 1] - rowptr[f] ? wmax : rowptr[f + 1] - rowptr[f];
+        total += wmax;
+    }
+    return total * 32;
+}
 
 // The pattern of K and the assembly gather lists for one ordering of the free nodes.
 struct RowSet {

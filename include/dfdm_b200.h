@@ -91,6 +91,10 @@ typedef struct dfdm_options {
 #define DFDM_FLAG_SPMV_MATRIX_FREE 1   /* PCG: K p straight from q over the node-edge incidence (8 E bytes per design) instead of
                                           the stored CSR values (8 nnz): 7 % faster SpMV on the quad grid, 0.8 % per evaluation */
 
+#define DFDM_FLAG_MG_NO_TAIL 2         /* PCG: keep the coarse multigrid levels on the multi-launch path (one kernel per level and
+                                          pass, cluster kernel at the bottom) instead of the one-CTA-per-design-pair tail kernel;
+                                          same arithmetic, for A/B measurements and tests */
+
 /* preconditioner of the PCG path */
 #define DFDM_PRECOND_AUTO 0
 #define DFDM_PRECOND_JACOBI 1      /* z = r / diag(K) */

@@ -478,3 +478,29 @@ def test_host_calls_pipeline_in_chunks_and_serialise_per_plan():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("nfree,batch", [(40, 6), (64, 2), (96, 34)])
+def test_tail_kernel_is_the_same_preconditioner_as_the_launch_per_level_path(nfree, batch):
+    """k_mg_tail (one CTA per design pair walks the coarse levels) against the launch-per-level path it replaces:
+    the same arithmetic in the same order, so the same iteration counts and the same answers to rounding."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(nfree)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.info["mg_levels"] >= 2
+    q = W.sample_q(q0, batch, seed=9, spread=0.5, relative=True)
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    res = {}
+    for name, flags in (("tail", 0), ("levels", _lib.FLAG_MG_NO_TAIL)):
+        ev = Evaluator(plan, loads, xyz[plan.fixed], solver="pcg", flags=flags)
+        out = ev.loss_and_grad(prog, q, outputs=("xyz",))
+        assert np.all(out["status"].cpu().numpy() == 0)
+        res[name] = (out["xyz"].cpu().numpy(), out["dq"].cpu().numpy(), _lib.last_pcg_iterations())
+    assert res["tail"][2] == res["levels"][2]
+    assert _rel(res["tail"][0], res["levels"][0]) < 1e-11
+    assert _rel(res["tail"][1], res["levels"][1]) < 1e-10
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    loss, dq, st = sm.loss_and_grad_edge_length(q[batch - 1], lengths0, 1.0, 0.1)
+    assert _rel(res["tail"][0][batch - 1], st.xyz) < TOL_X and _rel(res["tail"][1][batch - 1], dq) < TOL_G

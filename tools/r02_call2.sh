@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tail or grid256 or pcg" > gpurun_out/r02_pytest2.log 2>&1; echo "pytest rc $?"
+tail -15 gpurun_out/r02_pytest2.log
+
+for t in 0 6144 16384; do
+  DFDM_MG_TAIL=$t timeout 600 python bench.py --no-cpu --steps 10 > gpurun_out/r02_bench_tail$t.json 2> gpurun_out/r02_bench_tail$t.err; echo "tail $t rc $?"
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/r02_bench_tail*.json")):
+    try:
+        d = json.load(open(f))
+        print(f, "value %.5g e2e %.5g ms %.3f iters %s frac %.3f" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["config"].get("pcg_iterations"), d["roofline"]["frac"]))
+        for k in d.get("kernels", []): print("   %-50s %8.4f ms %7.0f GB/s share %.3f" % (k["kernel"], k["avg_ms"], k["achieved_gbs"], k["share_of_step"]))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
