@@ -294,6 +294,10 @@ def gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        for ev_ in starts + ends:                       # events are created lazily: do it outside the timed steps
+            ev_.record()
+        step()                                          # untimed pre-roll: the device is busy (clocks up) when the first timed step starts
+        step()
         for k in range(args.steps):
             if flush:
                 flush_buf.fill_(float(k))
@@ -358,7 +362,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]},
                        "pcg_rtol": args.pcg_rtol or _lib.PCG_RTOL_DEFAULT, "pcg_rtol_adjoint": args.pcg_rtol_adjoint or _lib.PCG_RTOL_ADJOINT_DEFAULT,
-                       "pcg_rtol_note": "loosest stop tests that keep coordinates within 1e-10 and gradients within 1e-8 of SuperLU at this size (tools/rtol_sweep.py, profiles/)",
+                       "pcg_rtol_note": "stop tests calibrated against SuperLU / the dense oracle with a tenfold margin to the 1e-9 / 1e-7 contract (include/dfdm_b200.h, tools/rtol_sweep.py)",
                        "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded; exchange per step: %s)" % (world, sharded.collective if world > 1 else "none"),
                        "exchange": args.exchange if world > 1 else None, "gather_ok": gather_ok,

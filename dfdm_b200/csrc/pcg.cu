@@ -1134,49 +1134,43 @@ __global__ void __launch_bounds__(kBottomThreads, 1) k_mg_bottom(BottomArgs a, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// The coarse levels from level `tail` down in ONE launch per visit: k_mg_tail.
+// The small coarse levels (from level `tail` down) in ONE launch per visit: k_mg_tail.
 //
 // Designs never couple, so the whole sub-cycle below a level (W revisits included) can be walked by ONE CTA per design
-// pair with nothing but block barriers between its stages - no kernel boundaries, no cluster or grid barriers.  What that
-// needs is a layout in which one pair's data is contiguous: the operators of the tail levels are repacked once per
-// evaluation (k_pack_pairs) from the batch-interleaved arrays into PAIR-MAJOR sliced-ELL tables (float2 = the two designs
-// of the pair; rows in slices of 32, padded per slice, so a warp reads 256 consecutive bytes per matrix position).
-// Every vector that is GATHERED through the column indices lives in shared memory (a gather of 8-byte words from
-// global memory costs one L1 tag look-up per lane; measured, that - not bandwidth or latency - bounded the first version
-// of this kernel): right-hand sides, solutions and W-cycle residuals of the levels below the top one, and ONE staging
-// buffer for the top level that holds, in turn, its right-hand side, its first solution and its residual.  Vectors
-// that a thread reads only at its own row (t, 1/diag, the top level's own-row copies) are pair-major global arrays,
-// read and written coalesced.  The right-hand side comes in and the solution goes out in the interleaved layout of the
-// levels above.  Arithmetic and summation order are those of k_mg_down / k_mg_up / k_mg_resid and the dense coarsest
-// product, so the preconditioner (and the iteration counts) are unchanged.
+// pair with nothing but block barriers between its stages - no kernel boundaries, no cluster or grid barriers.  Measured
+// on the first versions of this kernel (profiles/README.md): a stage of a small level costs one dependent global load
+// after the other (~1 000 cycles each, L2 hit or not), and gathers of 8-byte words from global memory cost an L1 tag
+// look-up per lane.  So EVERYTHING the stages touch is staged into shared memory once per launch and stays there:
+// per level the operator as a sliced-ELL table (float2 = the two designs of the pair; rows in slices of 32 padded per
+// slice; column / aggregate indices as 16-bit words), 1/diag, the slice offsets and aggregate maps, and the vectors
+// b, z, t (and the W-cycle residual); for the coarsest level its explicit inverse.  Only the top level keeps its
+// own-row copies of b, z and the residual in (pair-major, coalesced) global arrays: in shared memory it has ONE staging
+// buffer that holds, in turn, whichever of the three the next stage gathers from.  The operators are repacked from the
+// batch-interleaved arrays into pair-major tables once per evaluation (k_pack_pairs); the right-hand side comes in and
+// the solution goes out in the interleaved layout of the levels above.  Arithmetic and summation order are those of
+// k_mg_down / k_mg_up / k_mg_resid and the dense coarsest product: the preconditioner is unchanged.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTailMax = 8;              // levels inside the tail kernel, the coarsest (dense inverse) included
 constexpr int kTailThreads = 1024;
-constexpr int kTailRowsMax = 8192;       // largest level the workspace provides pair-major arrays for
-#ifndef DFDM_TAIL_U
-#define DFDM_TAIL_U 5
-#endif
-constexpr int kTailU = DFDM_TAIL_U;      // matrix positions in flight per thread
+constexpr int kTailRowsMax = 4096;       // largest level the workspace provides pair-major arrays for
 
 struct TailLevel {
     int n, nc;                           // rows of this level / of the next coarser one
     int twice;                           // W level: two cycles per visit
     float over;                          // scaling of this level's coarse-grid correction
-    const int32_t *off, *col, *aggc, *agg, *mem_ptr;
-    const float2* vals;                  // [pairs][ent] K, sliced ELL, zero where padded
-    const float2* vals_s;                // [pairs][ent] K D^-1
+    int slices, ent;                     // sliced ELL: slices of 32 rows, ent = 32 * sum of the slice widths
+    const int32_t *off, *col, *aggc, *agg, *mem_ptr;    // device index tables (design independent)
+    const float2* vals;                  // [pairs][ent] K, zero where padded
     const float2* d;                     // [pairs][n]   1 / diag
-    int64_t ent;
-    float2* t;                           // [pairs][3 n] global, own-row only
-    // gathered vectors: offsets (float2) into shared memory; below the top level b, z and r2 each have their own,
-    // on the top level they share ONE staging buffer (sb == sz == sr) and the own-row copies live in gb / gz / gr
-    int sb, sz, sr;
-    float2 *gb, *gz, *gr;                // [pairs][3 n] global own-row copies (top level only; null below)
+    // byte offsets into shared memory
+    int s_off, s_mem, s_agg, s_col, s_aggc, s_vals, s_d, s_b, s_z, s_r, s_t;
+    float2 *gb, *gz, *gr;                // top level only: [pairs][3 n] own-row copies (s_b == s_z == s_r: one staging buffer)
 };
 struct TailArgs {
     int count;                           // levels, the coarsest last
     TailLevel L[kTailMax];
     const float2* inv;                   // [pairs][n * n], (j n + i)
+    int s_inv;
     float omega;
     long long* trace;                    // tuning only (DFDM_TAIL_TRACE): CTA 0 logs (tag, clock) after every stage
 };
@@ -1215,50 +1209,67 @@ __global__ void __launch_bounds__(256) k_pack_pairs(const float* __restrict__ sr
     }
 }
 
-// acc[c] += sum_u vals(f, u) * x[c][col(f, u)] over row f of the sliced table; x is in SHARED memory
-__device__ __forceinline__ void tail_row(const int32_t* __restrict__ off, const int32_t* __restrict__ coltab, const float2* __restrict__ vals,
-                                         const float2* x, int nx, int f, float2 (&acc)[3]) {
-    constexpr int U = kTailU;
+// pointers of one level into shared memory
+struct TailSm {
+    const int32_t *off, *mem;
+    const uint16_t *agg, *col, *aggc;
+    const float2 *vals, *d;
+    float2 *b, *z, *r, *t;
+};
+__device__ __forceinline__ TailSm tail_sm(const TailLevel& L, char* sm) {
+    TailSm p;
+    p.off = reinterpret_cast<const int32_t*>(sm + L.s_off);
+    p.mem = reinterpret_cast<const int32_t*>(sm + L.s_mem);
+    p.agg = reinterpret_cast<const uint16_t*>(sm + L.s_agg);
+    p.col = reinterpret_cast<const uint16_t*>(sm + L.s_col);
+    p.aggc = reinterpret_cast<const uint16_t*>(sm + L.s_aggc);
+    p.vals = reinterpret_cast<const float2*>(sm + L.s_vals);
+    p.d = reinterpret_cast<const float2*>(sm + L.s_d);
+    p.b = reinterpret_cast<float2*>(sm + L.s_b);
+    p.z = reinterpret_cast<float2*>(sm + L.s_z);
+    p.r = reinterpret_cast<float2*>(sm + L.s_r);
+    p.t = reinterpret_cast<float2*>(sm + L.s_t);
+    return p;
+}
+
+// acc[c] += sum_u vals(f, u) [* d(col)] * x[c][col(f, u)] over row f of the sliced table; everything in shared memory
+template <bool SCALE>
+__device__ __forceinline__ void tail_row(const int32_t* off, const uint16_t* coltab, const float2* vals, const float2* d, const float2* x,
+                                         int nx, int f, float2 (&acc)[3]) {
     const int sl = f >> 5, lane = f & 31;
     const int o0 = off[sl], w = off[sl + 1] - o0;
-    for (int u0 = 0; u0 < w; u0 += U) {
-        int col[U];
-        float2 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = (o0 + min(u0 + u, w - 1)) * 32 + lane;
-            col[u] = __ldg(coltab + idx);
-            v[u] = __ldg(vals + idx);
+#pragma unroll 2
+    for (int u = 0; u < w; ++u) {
+        const int idx = (o0 + u) * 32 + lane;
+        const int col = coltab[idx];
+        float2 v = vals[idx];
+        if (SCALE) {
+            const float2 dc = d[col];
+            v.x *= dc.x;
+            v.y *= dc.y;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (u0 + u >= w) v[u] = make_float2(0.0f, 0.0f);
-            const float2 x0 = x[col[u]], x1 = x[nx + col[u]], x2 = x[2 * nx + col[u]];
-            acc[0].x += v[u].x * x0.x; acc[0].y += v[u].y * x0.y;
-            acc[1].x += v[u].x * x1.x; acc[1].y += v[u].y * x1.y;
-            acc[2].x += v[u].x * x2.x; acc[2].y += v[u].y * x2.y;
-        }
+        const float2 x0 = x[col], x1 = x[nx + col], x2 = x[2 * nx + col];
+        acc[0].x += v.x * x0.x; acc[0].y += v.y * x0.y;
+        acc[1].x += v.x * x1.x; acc[1].y += v.y * x1.y;
+        acc[2].x += v.x * x2.x; acc[2].y += v.y * x2.y;
     }
 }
 
 // down pass of one level: t = (K D^-1) rhs; the smoothed residual rhs - w t is parked, then summed over every aggregate.
-// rhs_g: gather source (shared); rhs_o: the same vector for own-row reads; bc: right-hand side of the next level (shared)
-__device__ void tail_down(const TailLevel& L, const float2* vals_s, const float2* rhs_g, const float2* rhs_o, float2* t, float2* park,
-                          float2* bc, float omega) {
-    const int n = L.n, nc = L.nc;
+// rhs_g: gather source (shared); rhs_o: the same vector for own-row reads (global on the top level); bc: next level's b
+__device__ void tail_down(int n, int nc, const TailSm& P, const float2* rhs_g, const float2* rhs_o, float2* park, float2* bc, float omega) {
     for (int f = threadIdx.x; f < n; f += kTailThreads) {
+        const float2 b0 = rhs_o[f], b1 = rhs_o[n + f], b2 = rhs_o[2 * n + f];     // issued before the row product: may be global
         float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        tail_row(L.off, L.col, vals_s, rhs_g, n, f, acc);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float2 b = rhs_o[c * n + f];
-            t[c * n + f] = acc[c];
-            park[c * n + f] = make_float2(b.x - omega * acc[c].x, b.y - omega * acc[c].y);
-        }
+        tail_row<true>(P.off, P.col, P.vals, P.d, rhs_g, n, f, acc);
+        P.t[f] = acc[0]; P.t[n + f] = acc[1]; P.t[2 * n + f] = acc[2];
+        park[f] = make_float2(b0.x - omega * acc[0].x, b0.y - omega * acc[0].y);
+        park[n + f] = make_float2(b1.x - omega * acc[1].x, b1.y - omega * acc[1].y);
+        park[2 * n + f] = make_float2(b2.x - omega * acc[2].x, b2.y - omega * acc[2].y);
     }
     __syncthreads();
     for (int I = threadIdx.x; I < nc; I += kTailThreads) {
-        const int m0 = L.mem_ptr[I], m1 = L.mem_ptr[I + 1];
+        const int m0 = P.mem[I], m1 = P.mem[I + 1];
         float2 rc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         for (int m = m0; m < m1; ++m)
 #pragma unroll
@@ -1274,35 +1285,38 @@ __device__ void tail_down(const TailLevel& L, const float2* vals_s, const float2
 }
 
 // up pass: out (+)= x' + w D^-1 (rhs - K x'), x' = w D^-1 rhs + s P e.  e: solution of the next level (shared).
-// The result goes to out (own rows; prev is read there when accumulating), to out2 (nullable: the staging buffer) and,
-// on the way out of the kernel, to the interleaved array of the level above (out_il, nullable).
-__device__ void tail_up(const TailLevel& L, const float2* vals, const float2* d, const float2* rhs_o, const float2* t, const float2* e,
-                        float2* out, float2* out2, float2* out_il, size_t il_stride, bool accumulate, float omega) {
-    const int n = L.n, nc = L.nc;
-    const float over = L.over;
+// The result goes to out (own rows; the previous value is read there when accumulating), to out2 (nullable: the staging
+// buffer) or, on the way out of the kernel, to the interleaved array of the level above (out_il).
+__device__ void tail_up(int n, int nc, float over, const TailSm& P, const float2* rhs_o, const float2* e, float2* out, float2* out2,
+                        float2* out_il, size_t il_stride, bool accumulate, float omega) {
     for (int f = threadIdx.x; f < n; f += kTailThreads) {
-        float2 sacc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        tail_row(L.off, L.aggc, vals, e, nc, f, sacc);
-        const float2 wd = d[f];
-        const int I = L.agg[f];
+        float2 b[3], prev[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float2 b = rhs_o[c * n + f], tc = t[c * n + f], ec = e[c * nc + I];
+            b[c] = rhs_o[c * n + f];
+            prev[c] = accumulate ? out[c * n + f] : make_float2(0.f, 0.f);
+        }
+        float2 sacc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        tail_row<false>(P.off, P.aggc, P.vals, nullptr, e, nc, f, sacc);
+        const float2 wd = P.d[f];
+        const int I = P.agg[f];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 tc = P.t[c * n + f], ec = e[c * nc + I];
             float2 z;
             {
                 const float w1 = omega * wd.x;
-                const float xn = w1 * b.x + over * ec.x;
-                z.x = xn + w1 * (b.x - omega * tc.x - over * sacc[c].x);
+                const float xn = w1 * b[c].x + over * ec.x;
+                z.x = xn + w1 * (b[c].x - omega * tc.x - over * sacc[c].x);
             }
             {
                 const float w1 = omega * wd.y;
-                const float xn = w1 * b.y + over * ec.y;
-                z.y = xn + w1 * (b.y - omega * tc.y - over * sacc[c].y);
+                const float xn = w1 * b[c].y + over * ec.y;
+                z.y = xn + w1 * (b[c].y - omega * tc.y - over * sacc[c].y);
             }
             if (accumulate) {
-                const float2 prev = out[c * n + f];
-                z.x += prev.x;
-                z.y += prev.y;
+                z.x += prev[c].x;
+                z.y += prev[c].y;
             }
             if (out_il) out_il[(size_t)(f * 3 + c) * il_stride] = z;
             else out[c * n + f] = z;
@@ -1313,35 +1327,85 @@ __device__ void tail_up(const TailLevel& L, const float2* vals, const float2* d,
 }
 
 // r2 = rhs - K x  (x gathered from shared memory)
-__device__ void tail_resid(const TailLevel& L, const float2* vals, const float2* rhs_o, const float2* x_g, float2* r2) {
-    const int n = L.n;
+__device__ void tail_resid(int n, const TailSm& P, const float2* rhs_o, const float2* x_g, float2* r2) {
     for (int f = threadIdx.x; f < n; f += kTailThreads) {
+        const float2 b0 = rhs_o[f], b1 = rhs_o[n + f], b2 = rhs_o[2 * n + f];
         float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        tail_row(L.off, L.col, vals, x_g, n, f, acc);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float2 b = rhs_o[c * n + f];
-            r2[c * n + f] = make_float2(b.x - acc[c].x, b.y - acc[c].y);
-        }
+        tail_row<false>(P.off, P.col, P.vals, nullptr, x_g, n, f, acc);
+        r2[f] = make_float2(b0.x - acc[0].x, b0.y - acc[0].y);
+        r2[n + f] = make_float2(b1.x - acc[1].x, b1.y - acc[1].y);
+        r2[2 * n + f] = make_float2(b2.x - acc[2].x, b2.y - acc[2].y);
     }
     __syncthreads();
 }
 
+// coalesced copies into shared memory, four loads in flight per thread
+template <typename TS, typename TD>
+__device__ __forceinline__ void tail_stage(const TS* __restrict__ src, TD* dst, int count) {
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < count; i0 += U * kTailThreads) {
+        TS v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTailThreads;
+            if (i < count) v[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTailThreads;
+            if (i < count) dst[i] = (TD)v[u];
+        }
+    }
+}
+__device__ __forceinline__ void tail_stage2(const float2* __restrict__ src, float2* dst, int count) {
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < count; i0 += U * kTailThreads) {
+        float2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTailThreads;
+            if (i < count) v[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kTailThreads;
+            if (i < count) dst[i] = v[u];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, const float* __restrict__ rhs_il, float* __restrict__ out_il,
                                                             const int32_t* __restrict__ n_active) {
-    pdl_wait();
-    if (__ldcg(&n_active[1]) == 0) return;
-    extern __shared__ float2 tsm[];
+    extern __shared__ __align__(16) char tsm[];
     const int tid = threadIdx.x;
     const int pairs = B >> 1;
     const int last = a.count - 1;
+    // the design-independent index tables do not depend on the kernels before this one: staged ahead of the dependency wait
+    for (int k = 0; k < last; ++k) {
+        const TailLevel& L = a.L[k];
+        tail_stage(L.off, reinterpret_cast<int32_t*>(tsm + L.s_off), L.slices + 1);
+        tail_stage(L.mem_ptr, reinterpret_cast<int32_t*>(tsm + L.s_mem), L.nc + 1);
+        tail_stage(L.agg, reinterpret_cast<uint16_t*>(tsm + L.s_agg), L.n);
+        tail_stage(L.col, reinterpret_cast<uint16_t*>(tsm + L.s_col), L.ent);
+        tail_stage(L.aggc, reinterpret_cast<uint16_t*>(tsm + L.s_aggc), L.ent);
+    }
+    pdl_wait();
+    if (__ldcg(&n_active[1]) == 0) return;
     const float omega = a.omega;
     const size_t il_stride = (size_t)B / 2;                 // float2 elements between consecutive (row, coordinate) entries
     int tr_n = 0;
     TAIL_MARK(0);
     for (int pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        // ---- this pair's operators into shared memory -------------------------------------------------------------
+        for (int k = 0; k < last; ++k) {
+            const TailLevel& L = a.L[k];
+            tail_stage2(L.vals + (size_t)pair * L.ent, reinterpret_cast<float2*>(tsm + L.s_vals), L.ent);
+            tail_stage2(L.d + (size_t)pair * L.n, reinterpret_cast<float2*>(tsm + L.s_d), L.n);
+        }
+        const int ncst = a.L[last].n;
+        tail_stage2(a.inv + (size_t)pair * ncst * ncst, reinterpret_cast<float2*>(tsm + a.s_inv), ncst * ncst);
         const int n0 = a.L[0].n;
-        float2* const S = tsm + a.L[0].sb;                  // staging buffer of the top level
+        float2* const S = reinterpret_cast<float2*>(tsm + a.L[0].s_b);      // staging buffer of the top level
         float2* const gb0 = a.L[0].gb + (size_t)pair * 3 * n0;
         float2* const gz0 = a.L[0].gz + (size_t)pair * 3 * n0;
         float2* const gr0 = a.L[0].gr + (size_t)pair * 3 * n0;
@@ -1377,23 +1441,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, 
             const TailLevel& L = a.L[k];
             if (k == last) {                               // dense product with the explicit inverse
                 const int nn = L.n;
-                const float2* inv = a.inv + (size_t)pair * nn * nn;
-                const float2* b = tsm + L.sb;
-                float2* e = tsm + L.sz;
+                const float2* inv = reinterpret_cast<const float2*>(tsm + a.s_inv);
+                const float2* b = reinterpret_cast<const float2*>(tsm + L.s_b);
+                float2* e = reinterpret_cast<float2*>(tsm + L.s_z);
                 for (int idx = tid; idx < 3 * nn; idx += kTailThreads) {
                     const int c = idx / nn, i = idx - c * nn;
                     float2 s = make_float2(0.f, 0.f);
-                    constexpr int UC = 10;
-                    for (int j0 = 0; j0 < nn; j0 += UC) {
-                        float2 wv[UC];
-#pragma unroll
-                        for (int u = 0; u < UC; ++u) wv[u] = j0 + u < nn ? __ldg(inv + (size_t)(j0 + u) * nn + i) : make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int u = 0; u < UC; ++u) {
-                            const float2 x = b[c * nn + min(j0 + u, nn - 1)];
-                            s.x += wv[u].x * x.x;
-                            s.y += wv[u].y * x.y;
-                        }
+#pragma unroll 4
+                    for (int j = 0; j < nn; ++j) {
+                        const float2 wv = inv[j * nn + i], x = b[c * nn + j];
+                        s.x += wv.x * x.x;
+                        s.y += wv.y * x.y;
                     }
                     e[idx] = s;
                 }
@@ -1403,38 +1461,32 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, 
                 --k;
                 continue;
             }
-            const int n = L.n;
+            const int n = L.n, nc = L.nc;
             const bool top = k == 0;
-            const float2* vals = L.vals + (size_t)pair * L.ent;
-            const float2* vals_s = L.vals_s + (size_t)pair * L.ent;
-            const float2* d = L.d + (size_t)pair * n;
-            float2* t = L.t + (size_t)pair * 3 * n;
-            float2* sb = tsm + L.sb;
-            float2* sz = tsm + L.sz;
-            float2* sr = tsm + L.sr;
-            float2* bnext = tsm + a.L[k + 1].sb;
-            const float2* znext = tsm + a.L[k + 1].sz;
+            const TailSm P = tail_sm(L, tsm);
+            float2* bnext = reinterpret_cast<float2*>(tsm + a.L[k + 1].s_b);
+            const float2* znext = reinterpret_cast<const float2*>(tsm + a.L[k + 1].s_z);
             if (phase[k] == 0) {
                 // first cycle: residuals are parked where the solution will go
-                tail_down(L, vals_s, sb, top ? gb0 : sb, t, top ? gz0 : sz, bnext, omega);
+                tail_down(n, nc, P, P.b, top ? gb0 : P.b, top ? gz0 : P.z, bnext, omega);
                 TAIL_MARK(100 + k);
                 phase[k] = 1;
                 ++k;
                 phase[k] = 0;
             } else if (phase[k] == 1) {
                 const bool final_pass = top && !L.twice;
-                tail_up(L, vals, d, top ? gb0 : sb, t, znext, top ? gz0 : sz, (top && L.twice) ? S : nullptr,
+                tail_up(n, nc, L.over, P, top ? gb0 : P.b, znext, top ? gz0 : P.z, (top && L.twice) ? S : nullptr,
                         final_pass ? reinterpret_cast<float2*>(out_il) + pair : nullptr, il_stride, false, omega);
                 TAIL_MARK(200 + k);
                 if (L.twice) {                             // second cycle on the residual of the first
-                    tail_resid(L, vals, top ? gb0 : sb, top ? S : sz, top ? gr0 : sr);
+                    tail_resid(n, P, top ? gb0 : P.b, top ? S : P.z, top ? gr0 : P.r);
                     TAIL_MARK(300 + k);
                     if (top) {                             // the staging buffer now takes the residual (it was being gathered until here)
                         for (int idx = tid; idx < 3 * n; idx += kTailThreads) S[idx] = gr0[idx];
                         __syncthreads();
                     }
                     // the first right-hand side is dead: its storage parks the residuals of this pass
-                    tail_down(L, vals_s, top ? S : sr, top ? gr0 : sr, t, top ? gb0 : sb, bnext, omega);
+                    tail_down(n, nc, P, top ? S : P.r, top ? gr0 : P.r, top ? gb0 : P.b, bnext, omega);
                     TAIL_MARK(400 + k);
                     phase[k] = 2;
                     ++k;
@@ -1444,7 +1496,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, 
                     --k;
                 }
             } else {
-                tail_up(L, vals, d, top ? gr0 : sr, t, znext, top ? gz0 : sz, nullptr,
+                tail_up(n, nc, L.over, P, top ? gr0 : P.r, znext, top ? gz0 : P.z, nullptr,
                         top ? reinterpret_cast<float2*>(out_il) + pair : nullptr, il_stride, true, omega);
                 TAIL_MARK(500 + k);
                 if (top) break;
@@ -1881,10 +1933,8 @@ struct MgBuffers {
     int tail_first = 0;                                // first level the workspace holds pair-major arrays for (0: none)
     int tail = 0;                                      // level the tail kernel takes over at in this evaluation (0: not used)
     float2* pv[kMaxMgLevels + 1] = {nullptr};          // operator, sliced ELL
-    float2* pvs[kMaxMgLevels + 1] = {nullptr};         // operator with scaled columns (K D^-1), sliced ELL
     float2* pd[kMaxMgLevels + 1] = {nullptr};          // 1 / diag
     float2* pb[kMaxMgLevels + 1] = {nullptr};
-    float2* pt[kMaxMgLevels + 1] = {nullptr};
     float2* pz[kMaxMgLevels + 1] = {nullptr};
     float2* pr[kMaxMgLevels + 1] = {nullptr};
     float2* pinv = nullptr;
@@ -1933,13 +1983,11 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
                 const int64_t nl = mg_n[l - 1];
                 if (l < mg_levels) {
                     w.mg.pv[l] = bump.take<float2>(mg_ent[l - 1] * pairs);
-                    w.mg.pvs[l] = bump.take<float2>(mg_ent[l - 1] * pairs);
                     w.mg.pd[l] = bump.take<float2>(nl * pairs);
-                    w.mg.pt[l] = bump.take<float2>(nl * 3 * pairs);
-                    w.mg.pr[l] = bump.take<float2>(nl * 3 * pairs);
+                    w.mg.pr[l] = bump.take<float2>(nl * 3 * pairs);    // own-row copies, used when the level is the tail's top
+                    w.mg.pb[l] = bump.take<float2>(nl * 3 * pairs);
+                    w.mg.pz[l] = bump.take<float2>(nl * 3 * pairs);
                 }
-                w.mg.pb[l] = bump.take<float2>(nl * 3 * pairs);
-                w.mg.pz[l] = bump.take<float2>(nl * 3 * pairs);
             }
             if (w.mg.tail_first) w.mg.pinv = bump.take<float2>(nc * nc * pairs);
         }
@@ -2074,16 +2122,52 @@ static int resolve_w_levels(const dfdm_options& opt, int n_levels) {
     return std::min(w_levels, std::max(0, n_levels - 1));
 }
 
-// shared memory (float2 elements) the tail kernel needs when it takes over at level l0: one staging buffer for the top
-// level, right-hand side and solution for every level below it, a residual for the W levels among those
-static int64_t tail_smem_elems(const MgDev& M, int l0, int w_levels) {
-    int64_t total = 3 * (int64_t)M.lv[l0 - 1].n;
-    for (int l = l0 + 1; l <= M.n_levels; ++l) {
+// Shared-memory layout of the tail kernel when it takes over at level l0 (byte offsets into `a`, total returned): per level
+// below the coarsest the index tables, the operator, 1/diag and the vectors; the top level's b / z / residual share one
+// staging buffer; the coarsest level has b, z and its explicit inverse.
+static int64_t tail_layout(const MgDev& M, int l0, int w_levels, TailArgs* a) {
+    int64_t cursor = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t at = cursor;
+        cursor += (bytes + 15) & ~(int64_t)15;
+        return (int)at;
+    };
+    const int nl = M.n_levels;
+    for (int l = l0; l <= nl; ++l) {
+        const int k = l - l0;
         const int64_t n = M.lv[l - 1].n;
-        total += 2 * ((3 * n + 1) & ~(int64_t)1);
-        if (l < M.n_levels && l <= w_levels) total += (3 * n + 1) & ~(int64_t)1;
+        TailLevel T{};
+        T.n = (int)n;
+        if (l < nl) {
+            const MgLevelDev& A = M.lv[l - 1];
+            const MgLevelDev& G = M.lv[l];
+            T.nc = G.n;
+            T.twice = l <= w_levels ? 1 : 0;
+            T.slices = A.tl_slices;
+            T.ent = (int)A.tl_ent;
+            T.s_off = take(4 * ((int64_t)A.tl_slices + 1));
+            T.s_mem = take(4 * ((int64_t)G.n + 1));
+            T.s_agg = take(2 * n);
+            T.s_col = take(2 * A.tl_ent);
+            T.s_aggc = take(2 * A.tl_ent);
+            T.s_vals = take(8 * A.tl_ent);
+            T.s_d = take(8 * n);
+            T.s_t = take(24 * n);
+            if (k == 0) {
+                T.s_b = T.s_z = T.s_r = take(24 * n);
+            } else {
+                T.s_b = take(24 * n);
+                T.s_z = take(24 * n);
+                T.s_r = T.twice ? take(24 * n) : T.s_b;
+            }
+        } else {
+            T.s_b = take(24 * n);
+            T.s_z = take(24 * n);
+            if (a) a->s_inv = take(8 * n * n); else take(8 * n * n);
+        }
+        if (a) a->L[k] = T;
     }
-    return total;
+    return cursor;
 }
 
 // Level at which the tail kernel takes over: the first coarse level with at most DFDM_MG_TAIL rows (default 6144; 0: off)
@@ -2093,7 +2177,7 @@ static int choose_tail(const MgDev& M, const PcgBuffers& w, const dfdm_options& 
     if (opt.flags & DFDM_FLAG_MG_NO_TAIL) return 0;
     static const int rows = [] {
         const char* v = std::getenv("DFDM_MG_TAIL");
-        int r = v ? std::atoi(v) : 6144;
+        int r = v ? std::atoi(v) : kTailRowsMax;
         return r < 0 ? 0 : (r > kTailRowsMax ? kTailRowsMax : r);
     }();
     if (!w.mg.tail_first || rows == 0) return 0;
@@ -2101,7 +2185,7 @@ static int choose_tail(const MgDev& M, const PcgBuffers& w, const dfdm_options& 
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
     const int w_levels = resolve_w_levels(opt, M.n_levels);
     for (int l = w.mg.tail_first; l < M.n_levels; ++l)          // at least two levels: l and the coarsest
-        if (M.lv[l - 1].n <= rows && tail_smem_elems(M, l, w_levels) * (int64_t)sizeof(float2) <= smem_max) return l;
+        if (M.lv[l - 1].n <= rows && M.lv[l - 1].n < 65536 && tail_layout(M, l, w_levels, nullptr) <= smem_max) return l;
     return 0;
 }
 
@@ -2157,8 +2241,6 @@ static int mg_setup(const PlanDev& P, const MgDev& M, const LaneCfg& base, int B
         for (int l = w.mg.tail; l < nl; ++l) {
             const MgLevelDev& A = M.lv[l - 1];
             int rc = pack_pairs(w.mg.vals[l], A.tl_src, A.tl_ent, B, w.mg.pv[l], st);
-            if (rc) return rc;
-            rc = pack_pairs(w.mg.vals_s[l], A.tl_src, A.tl_ent, B, w.mg.pvs[l], st);
             if (rc) return rc;
             rc = pack_pairs(w.mg.dinv[l], nullptr, A.n, B, w.mg.pd[l], st);
             if (rc) return rc;
@@ -2315,39 +2397,18 @@ static int mg_tail(const MgCtx& c, const mgf* rhs, mgf* out) {
         return p;
     }();
     a.trace = trace_buf;
-    int64_t cursor = 0;                                        // float2 elements of shared memory
-    auto take = [&](int64_t elems) {
-        const int at = (int)cursor;
-        cursor += (elems + 1) & ~(int64_t)1;
-        return at;
-    };
-    for (int k = 0; k < a.count; ++k) {
+    const size_t smem = (size_t)tail_layout(M, l0, c.w_levels, &a);
+    for (int k = 0; k < a.count - 1; ++k) {
         const int l = l0 + k;
         TailLevel& T = a.L[k];
-        T.n = M.lv[l - 1].n;
-        if (l < nl) {
-            const MgLevelDev& A = M.lv[l - 1];
-            const MgLevelDev& G = M.lv[l];
-            T.nc = G.n;
-            T.twice = l <= c.w_levels ? 1 : 0;
-            T.over = l < c.w_levels ? c.mp.over : c.mp_single.over;
-            T.off = A.tl_off; T.col = A.tl_col; T.aggc = A.tl_agg; T.agg = G.agg; T.mem_ptr = G.mem_ptr;
-            T.vals = w.mg.pv[l];
-            T.vals_s = w.mg.pvs[l];
-            T.d = w.mg.pd[l];
-            T.ent = A.tl_ent;
-            T.t = w.mg.pt[l];
-        }
-        if (k == 0) {
-            T.sb = T.sz = T.sr = take(3 * (int64_t)T.n);       // one staging buffer
-            T.gb = w.mg.pb[l]; T.gz = w.mg.pz[l]; T.gr = w.mg.pr[l];
-        } else {
-            T.sb = take(3 * (int64_t)T.n);
-            T.sz = take(3 * (int64_t)T.n);
-            T.sr = (l < nl && T.twice) ? take(3 * (int64_t)T.n) : T.sb;
-        }
+        const MgLevelDev& A = M.lv[l - 1];
+        const MgLevelDev& G = M.lv[l];
+        T.over = l < c.w_levels ? c.mp.over : c.mp_single.over;
+        T.off = A.tl_off; T.col = A.tl_col; T.aggc = A.tl_agg; T.agg = G.agg; T.mem_ptr = G.mem_ptr;
+        T.vals = w.mg.pv[l];
+        T.d = w.mg.pd[l];
+        if (k == 0) { T.gb = w.mg.pb[l]; T.gz = w.mg.pz[l]; T.gr = w.mg.pr[l]; }
     }
-    const size_t smem = (size_t)cursor * sizeof(float2);
     if (smem > 48 * 1024) {
         static std::mutex mu;
         static std::map<int, size_t> configured;

@@ -17,8 +17,10 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {c["name"]: c for c in golden_cases()}
-TOL_X = 1e-9
-TOL_G = 1e-7
+# DFDM_TEST_TOL_SCALE=0.1 checks that the solver defaults leave a tenfold margin to the contract
+TOL_SCALE = float(os.environ.get("DFDM_TEST_TOL_SCALE", "1"))
+TOL_X = 1e-9 * TOL_SCALE
+TOL_G = 1e-7 * TOL_SCALE
 STATE = ("xyz", "residuals", "vectors", "lengths", "forces")
 
 
@@ -467,8 +469,8 @@ def test_host_calls_pipeline_in_chunks_and_serialise_per_plan():
                 status = np.empty(count, dtype=np.int32)
                 ev.loss_and_grad_host(prog, np.ascontiguousarray(q[:count]), loss, dq, status)
                 assert np.all(status == 0)
-                assert np.allclose(loss, loss_ref[:count], rtol=1e-10, atol=0)
-                assert _rel(dq, dq_ref[:count]) < 1e-8
+                assert np.allclose(loss, loss_ref[:count], rtol=1e-9, atol=0)
+                assert _rel(dq, dq_ref[:count]) < TOL_G
         except Exception as exc:                       # noqa: BLE001 (reported to the main thread)
             errors.append(exc)
 

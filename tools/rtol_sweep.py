@@ -33,8 +33,10 @@ def main():
     designs = (0, 3, 7)
     ref = {b: sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.1) for b in designs}
     rows = []
-    for rf, ra in [(1e-12, 1e-12), (1e-11, 1e-11), (1e-10, 1e-10), (1e-9, 1e-9), (1e-8, 1e-8), (1e-7, 1e-7),
-                   (1e-11, 1e-9), (1e-11, 1e-8), (1e-11, 1e-7), (1e-10, 1e-8), (1e-10, 1e-7), (1e-10, 1e-6), (1e-12, 1e-6)]:
+    pairs = [(1e-12, 1e-12), (1e-11, 1e-11), (1e-10, 1e-10), (1e-9, 1e-9), (1e-8, 1e-8), (1e-7, 1e-7),
+             (1e-11, 1e-9), (1e-11, 1e-8), (1e-11, 1e-7), (1e-10, 1e-8), (1e-10, 1e-7), (1e-10, 1e-6), (1e-12, 1e-6),
+             (2e-11, 1e-7), (3e-11, 1e-7), (5e-11, 1e-7), (3e-11, 3e-7), (3e-11, 1e-6)]
+    for rf, ra in pairs:
         ev = Evaluator(plan, loads, xyz[plan.fixed], pcg_rtol=rf, pcg_rtol_adjoint=ra)
         out = ev.loss_and_grad(prog, q, outputs=("xyz",))
         it = _lib.last_pcg_iterations()
