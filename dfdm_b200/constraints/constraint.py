@@ -20,6 +20,8 @@ __all__ = ["Constraint", "NodeConstraint", "EdgeConstraint", "NetworkConstraint"
 
 def _cached_state(q, model):
     q = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+    if q.nbytes > (1 << 20):                 # batches: no comparison pass over hundreds of megabytes, just evaluate
+        return model(q)
     cache = getattr(model, "_state_cache", None)
     key = q.tobytes()
     if cache is None or cache[0] != key:

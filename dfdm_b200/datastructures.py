@@ -404,6 +404,9 @@ class FDNetwork(Network):
     """
     A force density network (reference: datastructures.py:9-139; same defaults, same accessors).
     """
+    # compas.data.Data.dtype = first two levels of the defining module + "/" + class name: the reference class lives in
+    # dfdm.datastructures.datastructures, so its files say "dfdm.datastructures/FDNetwork"
+    DTYPE = "dfdm.datastructures/FDNetwork"
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)

@@ -7,7 +7,13 @@ device goal table (kind, element row, weight, parameters) and the CUDA kernels c
 target, loss contribution and cotangents (include/dfdm_b200.h, DFDM_GOAL_*).
 
 ``goal(eqstate, model)`` (goal.py:23-33 in the reference) is kept for inspecting an already computed
-state on the host; it plays no part in ``Loss.__call__`` or in the gradient.
+state on the host; for the library goals it plays no part in ``Loss.__call__`` or in the gradient.
+
+USER-DEFINED goals (the reference differentiates any ``Goal`` subclass through autograd, goal.py:40-68): subclass
+``NodeGoal`` / ``EdgeGoal`` / ``NetworkGoal`` with the ``ScalarGoal`` / ``VectorGoal`` mix-ins, leave ``KIND`` unset
+and write ``prediction(eq_state, index)`` with torch operations - ``eq_state`` then holds torch tensors on the GPU
+that are attached to the CUDA path through ``dfdm_b200.autograd.EquilibriumFunction`` (forward: dfdm_forward,
+backward: dfdm_vjp).  ``Loss`` sends such goals down that route by itself; see losses.py.
 """
 import numpy as np
 
@@ -52,8 +58,8 @@ class Goal:
     def record(self, model):
         """``(kind, element row or None, weight, params)`` for dfdm_b200.engine.GoalProgram."""
         if self.KIND is None:
-            raise NotImplementedError("%s has no device kernel: only the goal classes of dfdm_b200.goals run on the GPU"
-                                      % type(self).__name__)
+            raise NotImplementedError("%s has no record in the device goal table; user-defined goals are evaluated on the torch "
+                                      "tape over the CUDA forward / adjoint (Loss does that by itself)" % type(self).__name__)
         return self.KIND, self.index(model), float(self._weight), self.params()
 
 

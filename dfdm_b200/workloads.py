@@ -275,6 +275,8 @@ def dome(num_sides=16, num_rings=6, diameter=1.0, offset_distance=0.03, q0_ring=
         network.edge_forcedensity(edge, q0_cross)
     network.attributes["edges_rings"] = edges_rings
     network.attributes["edges_cross"] = edges_cross
+    # the radial edges between ring i and ring i + 1 (examples/dome.py:137-142), lower node first
+    network.attributes["edges_cross_rings"] = [[(a, b) for a, b in zip(lower, upper)] for lower, upper in zip(rings[:-1], rings[1:])]
     return network
 
 

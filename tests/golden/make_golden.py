@@ -73,10 +73,10 @@ def _make_anp():
         return _t(a) if _torch_mode(a) else _np.array(a, dtype=dtype)
 
     def diag(a):
-        return torch.diag(a) if _torch_mode(a) else _np.diag(a)
+        return torch.diag(_t(a)) if _torch_mode(a) else _np.diag(a)
 
     def transpose(a):
-        return a.T if _torch_mode(a) else _np.transpose(a)
+        return _t(a).T if _torch_mode(a) else _np.transpose(a)
 
     def concatenate(seq, axis=0):
         if _torch_mode(*seq):
@@ -108,10 +108,10 @@ def _make_anp():
         return _t(a) * b if _torch_mode(a, b) else _np.multiply(a, b)
 
     def roll(a, shift, axis=None):
-        return torch.roll(a, shift, dims=axis) if _torch_mode(a) else _np.roll(a, shift, axis=axis)
+        return torch.roll(_t(a), shift, dims=axis) if _torch_mode(a) else _np.roll(a, shift, axis=axis)
 
     def reshape(a, shape):
-        return a.reshape(shape) if _torch_mode(a) else _np.reshape(a, shape)
+        return _t(a).reshape(shape) if _torch_mode(a) else _np.reshape(a, shape)
 
     def full(shape, value):
         return torch.full(tuple(shape), float(value), dtype=torch.float64) if _torch_mode() else _np.full(shape, value)

@@ -345,3 +345,21 @@ def test_coarse_cycle_bytes_counts_every_visit():
     assert abs(v - want) < 1e-6 * want
     assert bench.coarse_cycle_bytes(plan, 1) > 1.9 * v - 1e-9 or len(rows) < 3          # level 1 and everything below it twice
     assert bench.coarse_cycle_bytes(plan, 0) == bench.coarse_cycle_bytes(plan, 3)       # 0 means the default depth
+
+
+def test_compas_data_json_fixtures_are_read_and_written_back():
+    """Files in the layout compas.json_dump gives Data objects ({"dtype": "module/Class", "value": obj.data, "guid": ...};
+    Network.data with repr()-ed keys, 'dna' / 'dea' defaults, 'adjacency', 'max_node'), written by hand from COMPAS 1.x's
+    published serialisation - COMPAS itself is not installable here - as read by examples/history.py:95,104."""
+    import json
+    net = FDNetwork.from_json(os.path.join(GOLDEN, "compas_network_fixture.json"))
+    assert list(net.nodes()) == [0, 1, 2, 3] and list(net.edges()) == [(0, 1), (1, 2), (2, 3)]
+    assert list(net.nodes_fixed()) == [0, 3] and net.edges_forcedensities() == [-1.0, -2.0, -1.0]
+    assert net.node_load(1) == [0.0, 0.0, -0.5] and net.node_attribute(2, "rx") == 0.0        # defaults come from 'dna'
+    rec = OptimizationRecorder.from_json(os.path.join(GOLDEN, "compas_history_fixture.json"))
+    assert len(rec.history) == 3 and rec.history[1] == [-1.1, -1.9, -1.05]
+    # written back in the same envelope, keys as repr() strings
+    payload = json.loads(net.to_jsonstring())
+    assert payload["dtype"] == "dfdm.datastructures/FDNetwork" and set(payload["value"]) >= {"attributes", "dna", "dea", "node", "edge", "adjacency", "max_node"}
+    assert list(payload["value"]["node"]) == ["0", "1", "2", "3"] and payload["value"]["edge"]["1"] == {"2": {"q": -2.0}}
+    assert payload["value"]["adjacency"]["1"] == {"0": None, "2": None}

@@ -239,3 +239,71 @@ def test_peer_push_kernel_on_one_device():
     del views
     for p in ptrs:
         _lib.check(_lib.lib.dfdm_peer_free(C.c_void_p(p)))
+
+
+def test_user_defined_goal_and_loss_term_run_through_the_cuda_adjoint():
+    """The reference differentiates any Goal / LossTerm subclass through autograd (goals/goal.py:40-68, losses.py:22-31).
+    Here user code runs on a torch tape over EquilibriumFunction (forward dfdm_forward, backward dfdm_vjp); value and
+    gradient must equal the same functions on the oracle's CPU tape."""
+    import torch
+    from dfdm_b200.goals import NodeGoal, EdgeGoal, ScalarGoal, EdgeLengthGoal
+    from dfdm_b200.losses import LossTerm, SquaredError, L2Regularizer
+    from dfdm_b200.autograd import equilibrium
+
+    class NodeHeightGoal(ScalarGoal, NodeGoal):                 # user-defined: no KIND, torch prediction
+        def __init__(self, key, target, weight=1.0):
+            super().__init__(key=key, target=target, weight=weight)
+
+        def prediction(self, eq_state, index):
+            return eq_state.xyz[index, 2:3]
+
+    class EdgeStrainEnergyGoal(ScalarGoal, EdgeGoal):
+        def __init__(self, key, target, weight=1.0):
+            super().__init__(key=key, target=target, weight=weight)
+
+        def prediction(self, eq_state, index):
+            return torch.atleast_1d(eq_state.forces[index] ** 2 * eq_state.lengths[index])
+
+    class LogCoshError(LossTerm):                               # user-defined term: overrides loss(gstate)
+        def loss(self, gstate):
+            return self.alpha * torch.sum(gstate.weight * torch.log(torch.cosh(gstate.prediction - gstate.target)))
+
+    case = CASES["pringle"]
+    network = case["network"]
+    model = EquilibriumModel(network)
+    q = np.asarray(case["q"], dtype=np.float64)
+    free = list(network.nodes_free())
+    edges = list(network.edges())
+    heights = [NodeHeightGoal(k, target=0.3 + 0.01 * i, weight=1.0 + 0.1 * i) for i, k in enumerate(free[:7])]
+    energies = [EdgeStrainEnergyGoal(e, target=0.05, weight=2.0) for e in edges[3:9]]
+    lengths = [EdgeLengthGoal(e, target=0.4) for e in edges[:10]]
+    loss = Loss(SquaredError(lengths), SquaredError(heights, alpha=0.5), LogCoshError(energies, alpha=3.0), L2Regularizer(0.01))
+    value, grad = loss.value_and_grad(q, model)
+
+    # the same on the oracle's torch-f64 CPU tape
+    edges_a, is_fixed, xyz, loads = case_arrays(case)
+    s = O.Structure(len(is_fixed), edges_a, is_fixed)
+    omodel = O.Model(s, loads, xyz[s.fixed_nodes])
+    xp = O._torch_backend()
+    qt = torch.tensor(q, requires_grad=True)
+    st = omodel(qt, xp)
+    ni, ei = model.structure.node_index, model.structure.edge_index
+    ref = sum((st.lengths[ei[e]] - 0.4) ** 2 for e in edges[:10])
+    ref = ref + 0.5 * sum((1.0 + 0.1 * i) * (st.xyz[ni[k], 2] - (0.3 + 0.01 * i)) ** 2 for i, k in enumerate(free[:7]))
+    ref = ref + 3.0 * sum(2.0 * torch.log(torch.cosh(st.forces[ei[e]] ** 2 * st.lengths[ei[e]] - 0.05)) for e in edges[3:9])
+    ref = ref + 0.01 * torch.sum(qt ** 2)
+    gref, = torch.autograd.grad(ref, qt)
+    assert abs(value - float(ref)) < 1e-9 * abs(float(ref))
+    assert np.max(np.abs(grad - gref.numpy())) < 1e-7 * np.max(np.abs(gref.numpy()))
+
+    # the differentiable calculator on its own, batched: d/dq of a scalar of every state array
+    def scalar_of(state, dim):
+        return (state.xyz ** 2).sum() + 0.3 * state.lengths.sum() + (state.residuals[..., 2] * state.forces.mean(dim=dim, keepdim=True)).sum() \
+            + (state.vectors[..., 0] * state.forces).sum()
+
+    qb = torch.tensor(np.stack([q, 0.9 * q]), dtype=torch.float64, device="cuda", requires_grad=True)
+    scalar_of(equilibrium(qb, model), 1).backward()
+    for b, scale in enumerate((1.0, 0.9)):
+        qo = torch.tensor(scale * q, requires_grad=True)
+        go, = torch.autograd.grad(scalar_of(omodel(qo, xp), 0), qo)
+        assert np.max(np.abs(qb.grad[b].cpu().numpy() - go.numpy())) < 1e-7 * np.max(np.abs(go.numpy()))

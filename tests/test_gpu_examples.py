@@ -69,3 +69,86 @@ def test_sharded_ensemble_on_one_rank():
     assert start.shape == end.shape == (128,) and q_opt.shape[0] == 128
     assert np.all(end <= start) and end.mean() < 0.7 * start.mean()
     assert np.all(q_opt <= -1e-3 + 1e-12)
+
+
+# ---- the reference's own optimisers on the same scripts ------------------------------------------------------------
+
+GOLDEN_EXAMPLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "examples.npz")
+# keyword arguments of every example's main(): the ones tests/golden/make_example_golden.py ran the reference with
+EXAMPLE_RUNS = {
+    "arches": dict(vertical_comps=(0.2, 0.8), verbose=False),
+    "pillow": dict(maxiter=40, verbose=False),
+    "pringle": dict(maxiter=60, verbose=False),
+    "dome_constraints": dict(maxiter=40, verbose=False),
+    "monkey_saddle_constraints": dict(maxiter=40, verbose=False),
+    "dome": dict(maxiter=300, tol=1e-3, verbose=False),
+    "monkey_saddle": dict(maxiter=200, tol=1e-3, verbose=False),
+}
+# Relative tolerances on (loss, q, xyz) per example.  The optimisers are SciPy's in both runs and the gradients agree to
+# ~1e-12, so runs that CONVERGE land on the same optimum to the optimiser's own tolerance; runs cut off by maxiter
+# (pillow, dome_constraints with constraints, trust-constr) follow the same path only as far as rounding lets a
+# quasi-Newton iteration - their shapes are compared to the accuracy the measured differences (profiles/README.md) support.
+EXAMPLE_TOL = {
+    "arches": (1e-9, 1e-6, 1e-6),
+    "pillow": (1e-3, 1e-3, 1e-4),
+    "pringle": (1e-4, 1e-3, 1e-4),
+    "dome_constraints": (1e-3, 1e-3, 1e-4),
+    "monkey_saddle_constraints": (5e-2, 5e-2, 1e-2),
+    "dome": (1e-2, 5e-2, 1e-3),
+    "monkey_saddle": (1e-4, 1e-3, 1e-4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXAMPLE_RUNS))
+def test_example_reproduces_the_reference_run(name):
+    """Every constrained_fdm call of the example, in order, against the same call made by the reference's code."""
+    import dfdm_b200.equilibrium as EQ
+    gold = np.load(GOLDEN_EXAMPLES)
+    mod = _load(name)
+    calls = []
+    real = EQ.constrained_fdm
+
+    def recording(network, optimizer, loss, *args, **kwargs):
+        out = real(network, optimizer, loss, *args, **kwargs)
+        q = np.asarray(out.edges_forcedensities(), dtype=np.float64)
+        xyz = np.asarray([out.node_coordinates(k) for k in out.nodes()], dtype=np.float64)
+        from dfdm_b200.equilibrium import EquilibriumModel
+        calls.append({"q": q, "xyz": xyz, "loss": float(loss(q, EquilibriumModel(network)))})
+        return out
+
+    mod.constrained_fdm = recording
+    mod.main(**EXAMPLE_RUNS[name])
+    expected = sorted({int(k.split(".")[1]) for k in gold.files if k.startswith(name + ".")})
+    assert len(calls) == len(expected) > 0
+    tol_loss, tol_q, tol_x = EXAMPLE_TOL[name]
+    report = []
+    for i, c in enumerate(calls):
+        g = {key: gold["%s.%d.%s" % (name, i, key)] for key in ("q", "xyz", "loss")}
+        e_loss = abs(c["loss"] - float(g["loss"])) / max(abs(float(g["loss"])), 1e-12) if abs(float(g["loss"])) > 1e-9 else abs(c["loss"])
+        e_q = float(np.max(np.abs(c["q"] - g["q"])) / np.max(np.abs(g["q"])))
+        e_x = float(np.max(np.abs(c["xyz"] - g["xyz"])) / np.max(np.abs(g["xyz"])))
+        report.append((i, e_loss, e_q, e_x))
+    print("example %s vs reference run: (call, loss, q, xyz) relative differences: %s" % (name, report))
+    for i, e_loss, e_q, e_x in report:
+        assert e_loss < tol_loss and e_q < tol_q and e_x < tol_x, (name, report)
+
+
+def test_history_replays_the_recorded_optimisation(tmp_path):
+    """examples/monkey_saddle.py writes base / history / optimised JSON; examples/history.py replays them frame by frame."""
+    network, curves, reactions, targets, out_dir = _load("monkey_saddle").main(maxiter=30, tol=1e-3, out_dir=str(tmp_path), verbose=False)
+    assert set(curves) == {"Loss", "EdgeLengthGoal", "ReactionForceGoal", "LoadPathGoal", "L2Regularizer"}
+    total = curves["EdgeLengthGoal"] + curves["ReactionForceGoal"] + curves["LoadPathGoal"] + curves["L2Regularizer"]
+    assert np.allclose(total, curves["Loss"], rtol=1e-9)          # the terms add up to the loss at every recorded iterate
+    assert curves["Loss"][-1] < curves["Loss"][0]
+    frames, loadpaths, last = _load("history").main(in_dir=out_dir, verbose=False)
+    assert len(frames) == len(curves["Loss"]) > 1
+    assert np.allclose([f["loadpath"] for f in frames], loadpaths, rtol=1e-9)     # frame-by-frame loop == one batched evaluation
+    q_last = np.asarray(last.edges_forcedensities())
+    assert np.allclose(q_last, np.asarray(network.edges_forcedensities()), rtol=1e-12, atol=0)
+
+
+def test_dome_loss_terms_along_the_history():
+    networks, curves = _load("dome").main(maxiter=25, tol=1e-3, verbose=False, num_rings=12)
+    assert {"Loss", "SquaredError"} <= set(curves) and len(curves["Loss"]) > 1
+    assert np.allclose(curves["Loss"], curves["SquaredError"], rtol=1e-9)
+    assert curves["Loss"][-1] < curves["Loss"][0]
