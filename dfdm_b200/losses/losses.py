@@ -180,6 +180,16 @@ class Loss:
         self._last = (key, loss, dq) if key is not None else None
         return loss, dq
 
+    def value_and_grad_device(self, q, model):
+        """``q[B, E]`` torch tensor on the model's GPU -> (loss[B], dq[B, E]) torch tensors on the same GPU: nothing crosses
+        PCIe but the B status words.  The device-resident optimisers call this (optimization.BatchedLBFGS)."""
+        custom = [term for term in self.loss_terms if not isinstance(term, Regularizer) and not term.on_device()]
+        if custom:
+            raise NotImplementedError("user-defined goals / terms are evaluated design by design on the torch tape: use value_and_grad")
+        out = model.evaluator.loss_and_grad(self.program(model), q, grad=True)
+        Evaluator.raise_on_status(out["status"])
+        return out["loss"], out["dq"]
+
     def __call__(self, q, model):
         """The loss of design ``q[E]`` (a float) or of a batch ``q[B, E]`` (an array)."""
         return self._evaluate(q, model, grad=False)[0]

@@ -32,10 +32,27 @@ class Optimizer:
             print(f"Warning! {self.__class__.__name__} does not support constraints. I am ignoring them.")
         return ()
 
-    def minimize(self, network, loss, bounds=(None, None), constraints=None, maxiter=100, tol=1e-6, verbose=True, callback=None):
-        """Minimise ``loss`` over the edge force densities of ``network``; returns the optimal q[E]."""
+    def minimize(self, network, loss, bounds=(None, None), constraints=None, maxiter=100, tol=1e-6, verbose=True, callback=None, q0=None):
+        """
+        Minimise ``loss`` over the edge force densities of ``network``; returns the optimal q[E].
+
+        ``q0`` (not in the reference): a batch of starting points ``q0[B, E]`` - NumPy array or torch tensor - turns the call
+        into an ENSEMBLE optimisation: all designs are improved in lock step by the device-resident projected L-BFGS
+        (``BatchedLBFGS``; SciPy's sequential drivers cannot serve a batch), one batched CUDA evaluation per trial point,
+        and ``q_opt[B, E]`` comes back in the type it was given.  Constraint objects are not supported there.
+        """
         name = self.name
-        q = np.asarray(network.edges_forcedensities(), dtype=np.float64)
+        if q0 is not None and np.ndim(q0) == 2:
+            if constraints:
+                raise NotImplementedError("ensemble optimisation (q0[B, E]) handles bounds, not constraint objects")
+            model = self.model = EquilibriumModel(network)
+            batched = BatchedLBFGS(maxiter=maxiter, gtol=tol, ftol=min(tol * 1e-3, 1e-9))
+            q_opt, value = batched.minimize(model, loss, q0, bounds=bounds, callback=callback)
+            self.result = {"fun": value, "nit": batched.iterations, "nfev": batched.evaluations}
+            if verbose:
+                print(f"Lock-step L-BFGS over {len(q_opt)} designs: {batched.iterations} iterations, {batched.evaluations} batched evaluations")
+            return q_opt
+        q = np.asarray(network.edges_forcedensities(), dtype=np.float64) if q0 is None else np.asarray(q0, dtype=np.float64)
         model = self.model = EquilibriumModel(network)
 
         def fun(x):
@@ -185,133 +202,189 @@ class BatchedGradientDescent:
     """
     Lock-step projected gradient descent with Barzilai-Borwein steps over a batch of designs q[B, E]:
     every iteration is one batched CUDA evaluation of all designs (loss + gradient); the step and the
-    projection onto the bounds are elementwise.  For ensembles / parameter sweeps on one or many GPUs.
+    projection onto the bounds are elementwise torch operations on the evaluator's GPU - the state never
+    leaves the device (``Loss.value_and_grad_device``).  For ensembles / parameter sweeps on one or many GPUs.
     """
     def __init__(self, step=1e-2, maxiter=100, tol=1e-6):
         self.step, self.maxiter, self.tol = step, maxiter, tol
 
     def minimize(self, model, loss, q0, bounds=(None, None), callback=None):
-        lb = -np.inf if bounds[0] is None else bounds[0]
-        ub = np.inf if bounds[1] is None else bounds[1]
-        q = np.clip(np.array(q0, dtype=np.float64, copy=True), lb, ub)
-        value, grad = loss.value_and_grad(q, model)
-        step = np.full(q.shape[0], self.step)
-        history = [np.array(value)]
+        import torch
+        dev = model.evaluator.device
+        host = not isinstance(q0, torch.Tensor)
+        lb = -float("inf") if bounds[0] is None else float(bounds[0])
+        ub = float("inf") if bounds[1] is None else float(bounds[1])
+        q = (torch.as_tensor(np.asarray(q0, dtype=np.float64)) if host else q0.detach()).to(dev, torch.float64).clamp(lb, ub).clone()
+        value, grad = loss.value_and_grad_device(q, model)
+        value, grad = value.clone(), grad.clone()
+        step = torch.full((q.shape[0],), float(self.step), dtype=torch.float64, device=dev)
+        history = [value.clone()]
         for it in range(self.maxiter):
-            q_new = np.clip(q - step[:, None] * grad, lb, ub)
-            value_new, grad_new = loss.value_and_grad(q_new, model)
+            q_new = (q - step[:, None] * grad).clamp(lb, ub)
+            value_new, grad_new = loss.value_and_grad_device(q_new, model)
             worse = value_new > value
             # Barzilai-Borwein step per design; halve where the loss went up and keep the old iterate there
             s, y = q_new - q, grad_new - grad
-            sy = np.sum(s * y, axis=1)
-            bb = np.where(sy > 0, np.sum(s * s, axis=1) / np.where(sy > 0, sy, 1.0), step * 2.0)
-            step = np.where(worse, step * 0.5, np.clip(bb, 1e-12, 1e6))
+            sy = (s * y).sum(dim=1)
+            bb = torch.where(sy > 0, (s * s).sum(dim=1) / torch.where(sy > 0, sy, torch.ones_like(sy)), step * 2.0)
+            step = torch.where(worse, step * 0.5, bb.clamp(1e-12, 1e6))
             keep = ~worse
-            q[keep], grad[keep] = q_new[keep], grad_new[keep]
-            value = np.where(keep, value_new, value)
-            history.append(np.array(value))
+            q = torch.where(keep[:, None], q_new, q)
+            grad = torch.where(keep[:, None], grad_new, grad)
+            value = torch.where(keep, value_new, value)
+            history.append(value.clone())
             if callback is not None:
                 callback(q, value)
-            if np.all(np.abs(history[-2] - history[-1]) <= self.tol * np.maximum(1.0, np.abs(history[-1]))) and not np.any(worse):
+            done = ((history[-2] - history[-1]).abs() <= self.tol * history[-1].abs().clamp_min(1.0)).all() & ~worse.any()
+            if bool(done.item()):                      # the one host read of an iteration
                 break
-        self.history = history
+        self.history = [h.cpu().numpy() for h in history]
+        if host:
+            return q.cpu().numpy(), value.cpu().numpy()
         return q, value
 
 
 class BatchedLBFGS:
     """
-    Lock-step projected L-BFGS over a batch of designs ``q[B, E]`` with box bounds.
+    Lock-step projected L-BFGS over a batch of designs ``q[B, E]`` with box bounds, DEVICE RESIDENT.
 
     Every design keeps its own curvature pairs, step length and convergence flag; what is shared is the
     evaluation: one batched CUDA call per trial point returns the loss and gradient of all designs.  The
     search direction is the two-loop recursion on the free variables (those not pinned at a bound with
     the gradient pointing outward), the step is found by backtracking on the Armijo condition along the
-    projected path, and designs that have converged stop moving.  ``fun(q) -> (loss[B], grad[B, E])`` is
-    any callable with that contract; ``minimize(model, loss, q0, ...)`` builds it from a ``Loss``.
+    projected path, and designs that have converged stop moving.
+
+    The whole state - ``q``, gradients, the curvature pairs, step lengths, masks - lives in torch tensors on the
+    evaluator's GPU and the evaluation hands back device tensors (``Loss.value_and_grad_device``): nothing of size
+    ``B x E`` crosses PCIe during the optimisation; the host reads one flag per iteration ("any design still active?").
+    In a sharded run every rank optimises its own slice of the ensemble with its own state, so there is no traffic
+    between GPUs either (``group``: the flag is all-reduced so that the ranks leave the loop together).
+
+    ``fun(q) -> (loss[B], grad[B, E])`` is any callable with that contract on torch tensors (NumPy results are
+    accepted and converted: CPU tests); ``minimize(model, loss, q0, ...)`` builds it from a ``Loss``.
     """
-    def __init__(self, memory=8, maxiter=100, gtol=1e-6, ftol=1e-10, armijo=1e-4, max_backtracks=12):
+    def __init__(self, memory=8, maxiter=100, gtol=1e-6, ftol=1e-10, armijo=1e-4, max_backtracks=12, group=None):
         self.memory, self.maxiter, self.gtol, self.ftol = memory, maxiter, gtol, ftol
         self.armijo, self.max_backtracks = armijo, max_backtracks
+        self.group = group
 
-    def minimize(self, model, loss, q0, bounds=(None, None), callback=None):
-        return self.minimize_fun(lambda q: loss.value_and_grad(q, model), q0, bounds, callback)
+    def minimize(self, model, loss, q0, bounds=(None, None), callback=None, as_numpy=None):
+        import torch
+        device = model.evaluator.device
+        host = not isinstance(q0, torch.Tensor)
+        q0_t = torch.as_tensor(np.asarray(q0, dtype=np.float64)) if host else q0
+        q, f = self.minimize_fun(lambda x: loss.value_and_grad_device(x, model), q0_t.to(device=device, dtype=torch.float64), bounds, callback)
+        if as_numpy if as_numpy is not None else host:
+            return q.cpu().numpy(), f.cpu().numpy()
+        return q, f
 
     def minimize_fun(self, fun, q0, bounds=(None, None), callback=None):
-        lb = -np.inf if bounds[0] is None else bounds[0]
-        ub = np.inf if bounds[1] is None else bounds[1]
-        q = np.clip(np.array(q0, dtype=np.float64, copy=True), lb, ub)
+        import torch
+        host = not isinstance(q0, torch.Tensor)
+        q = (torch.as_tensor(np.array(q0, dtype=np.float64)) if host else q0.detach().clone()).to(torch.float64)
+        dev = q.device
+        lb = -float("inf") if bounds[0] is None else float(bounds[0])
+        ub = float("inf") if bounds[1] is None else float(bounds[1])
+        q = q.clamp(lb, ub)
         B, E = q.shape
-        f, g = fun(q)
-        f, g = np.array(f, dtype=np.float64), np.array(g, dtype=np.float64)
-        S, Y = [], []                                    # curvature pairs, each [B, E]; rho per design
-        active = np.ones(B, dtype=bool)
+
+        def call(x):
+            ft, gt = fun(x.cpu().numpy() if host else x)
+            ft = ft if isinstance(ft, torch.Tensor) else torch.as_tensor(np.asarray(ft, dtype=np.float64))
+            gt = gt if isinstance(gt, torch.Tensor) else torch.as_tensor(np.asarray(gt, dtype=np.float64))
+            return ft.to(dev, torch.float64).clone(), gt.to(dev, torch.float64).clone()
+
+        def any_true(mask):
+            flag = mask.any().to(torch.int32).reshape(1)
+            if self.group is not None or _dist_ready():
+                import torch.distributed as dist
+                if dev.type != "cuda" and dist.get_backend(self.group) == "nccl":
+                    return bool(flag.item())
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            return bool(flag.item())                      # the one host read of an iteration
+
+        f, g = call(q)
+        S, Y = [], []                                    # curvature pairs, each [B, E] on the device
+        active = torch.ones(B, dtype=torch.bool, device=dev)
+        zero = torch.zeros((), dtype=torch.float64, device=dev)
+        one = torch.ones((), dtype=torch.float64, device=dev)
         self.evaluations = 1
-        history = [f.copy()]
+        history = [f.clone()]
 
         def projected_gradient(q, g):
-            pg = g.copy()
-            pg[(q <= lb) & (g > 0)] = 0.0
-            pg[(q >= ub) & (g < 0)] = 0.0
-            return pg
+            return torch.where(((q <= lb) & (g > 0)) | ((q >= ub) & (g < 0)), zero, g)
 
         for it in range(self.maxiter):
             pg = projected_gradient(q, g)
-            active &= np.max(np.abs(pg), axis=1) > self.gtol
-            if not active.any():
+            active &= pg.abs().amax(dim=1) > self.gtol
+            if not any_true(active):
                 break
             free = pg != 0.0
             # two-loop recursion, vectorised over designs
-            d = pg.copy()
+            d = pg.clone()
             alphas = []
             for s_k, y_k in zip(reversed(S), reversed(Y)):
-                sy = np.sum(s_k * y_k, axis=1)
+                sy = (s_k * y_k).sum(dim=1)
                 ok = sy > 1e-300
-                a = np.where(ok, np.sum(s_k * d, axis=1) / np.where(ok, sy, 1.0), 0.0)
+                a = torch.where(ok, (s_k * d).sum(dim=1) / torch.where(ok, sy, one), zero)
                 d -= a[:, None] * y_k
                 alphas.append((a, ok, sy))
             if S:
-                sy = np.sum(S[-1] * Y[-1], axis=1)
-                yy = np.sum(Y[-1] * Y[-1], axis=1)
-                gamma = np.where((sy > 1e-300) & (yy > 0), sy / np.where(yy > 0, yy, 1.0), 1.0)
+                sy = (S[-1] * Y[-1]).sum(dim=1)
+                yy = (Y[-1] * Y[-1]).sum(dim=1)
+                gamma = torch.where((sy > 1e-300) & (yy > 0), sy / torch.where(yy > 0, yy, one), one)
                 d *= gamma[:, None]
             for (a, ok, sy), s_k, y_k in zip(reversed(alphas), S, Y):
-                b = np.where(ok, np.sum(y_k * d, axis=1) / np.where(ok, sy, 1.0), 0.0)
+                b = torch.where(ok, (y_k * d).sum(dim=1) / torch.where(ok, sy, one), zero)
                 d += (a - b)[:, None] * s_k
-            d = -np.where(free, d, 0.0)
-            slope = np.sum(pg * d, axis=1)
+            d = -torch.where(free, d, zero)
+            slope = (pg * d).sum(dim=1)
             bad = slope >= 0                              # not a descent direction: fall back to steepest descent
-            d[bad] = -pg[bad]
-            slope = np.sum(pg * d, axis=1)
+            d = torch.where(bad[:, None], -pg, d)
             # backtracking along the projected path; per-design step lengths, one batched evaluation per trial
-            t = np.ones(B) if S else np.minimum(1.0, 1.0 / np.maximum(np.max(np.abs(pg), axis=1), 1e-300))
-            todo = active.copy()
-            q_new, f_new, g_new = q.copy(), f.copy(), g.copy()
+            if S:
+                t = torch.ones(B, dtype=torch.float64, device=dev)
+            else:
+                t = torch.minimum(one, 1.0 / pg.abs().amax(dim=1).clamp_min(1e-300))
+            todo = active.clone()
+            q_new, f_new, g_new = q.clone(), f.clone(), g.clone()
             for _ in range(self.max_backtracks):
-                trial = np.where(todo[:, None], np.clip(q + t[:, None] * d, lb, ub), q_new)
-                ft, gt = fun(trial)
+                trial = torch.where(todo[:, None], (q + t[:, None] * d).clamp(lb, ub), q_new)
+                ft, gt = call(trial)
                 self.evaluations += 1
-                ft, gt = np.asarray(ft, dtype=np.float64), np.asarray(gt, dtype=np.float64)
-                decrease = np.sum(pg * (trial - q), axis=1)
-                accept = todo & np.isfinite(ft) & (ft <= f + self.armijo * decrease)
-                q_new[accept], f_new[accept], g_new[accept] = trial[accept], ft[accept], gt[accept]
+                decrease = (pg * (trial - q)).sum(dim=1)
+                accept = todo & torch.isfinite(ft) & (ft <= f + self.armijo * decrease)
+                q_new = torch.where(accept[:, None], trial, q_new)
+                g_new = torch.where(accept[:, None], gt, g_new)
+                f_new = torch.where(accept, ft, f_new)
                 todo &= ~accept
-                if not todo.any():
+                if not any_true(todo):
                     break
-                t = np.where(todo, 0.5 * t, t)
+                t = torch.where(todo, 0.5 * t, t)
             active &= ~todo                               # no acceptable step: that design is done
             s_k, y_k = q_new - q, g_new - g
-            moved = np.any(s_k != 0.0, axis=1)
-            small = np.abs(f - f_new) <= self.ftol * np.maximum(1.0, np.abs(f_new))
+            moved = (s_k != 0.0).any(dim=1)
+            small = (f - f_new).abs() <= self.ftol * f_new.abs().clamp_min(1.0)
             active &= ~(moved & small)
-            S.append(np.where(moved[:, None], s_k, 0.0))
-            Y.append(np.where(moved[:, None], y_k, 0.0))
+            S.append(torch.where(moved[:, None], s_k, zero))
+            Y.append(torch.where(moved[:, None], y_k, zero))
             if len(S) > self.memory:
                 S.pop(0)
                 Y.pop(0)
             q, f, g = q_new, f_new, g_new
-            history.append(f.copy())
+            history.append(f.clone())
             if callback is not None:
                 callback(q, f)
-        self.history = history
+        self.history = [h.cpu().numpy() for h in history]
         self.iterations = len(history) - 1
+        if host:
+            return q.cpu().numpy(), f.cpu().numpy()
         return q, f
+
+
+def _dist_ready():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False

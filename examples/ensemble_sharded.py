@@ -1,7 +1,9 @@
 """
 configs[3] of BASELINE.json in ensemble form: a batch of dome designs improved in lock step, sharded over the
 GPUs of one node (one process per GPU).  Designs are independent, so every rank optimises its own contiguous
-slice with no traffic at all; ONE all-gather at the end collects the optimal force densities and losses.
+slice with its optimiser state on its own GPU (device-resident lock-step L-BFGS): no design data crosses PCIe or NVLink
+during the optimisation - one flag per iteration keeps the ranks in step - and ONE all-gather at the end collects the
+optimal force densities and losses.
 
     python examples/ensemble_sharded.py                                   # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
@@ -45,17 +47,21 @@ def main(batch_per_gpu=512, maxiter=30, verbose=True):
     q_all = workloads.sample_q(q0, batch, seed=5, spread=0.2, relative=True)     # the same ensemble on every rank
     lo, hi = shard_bounds(batch, world, rank)
 
-    start = loss(q_all[lo:hi], model)
+    device = torch.device("cuda", local_rank)
+    q_local = torch.as_tensor(np.ascontiguousarray(q_all[lo:hi]), device=device)        # this rank's slice: on its GPU from here on
+    start, _ = loss.value_and_grad_device(q_local, model)
+    start = start.clone()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    optimizer = BatchedLBFGS(maxiter=maxiter)
-    q_opt, value_opt = optimizer.minimize(model, loss, q_all[lo:hi], bounds=(None, -1e-3))
+    optimizer = BatchedLBFGS(maxiter=maxiter)                  # state (q, gradients, curvature pairs) lives with the designs
+    q_opt, value_opt = optimizer.minimize(model, loss, q_local, bounds=(None, -1e-3))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 
-    device = torch.device("cuda", local_rank)
-    q_opt_all = gather_designs(torch.from_numpy(np.ascontiguousarray(q_opt)).to(device), batch)
-    value_all = gather_designs(torch.from_numpy(np.ascontiguousarray(value_opt)).to(device), batch)
-    start_all = gather_designs(torch.from_numpy(np.ascontiguousarray(start)).to(device), batch)
+    # the ONLY exchange of the run: the optimal force densities and losses of every rank, once, at the end
+    q_opt_all = gather_designs(q_opt.contiguous(), batch)
+    value_all = gather_designs(value_opt.contiguous(), batch)
+    start_all = gather_designs(start, batch)
     if verbose and rank == 0:
         print(f"{batch} dome designs on {world} GPU(s): mean loss {float(start_all.mean()):.5f} -> {float(value_all.mean()):.5f} "
               f"in {optimizer.iterations} lock-step L-BFGS iterations, {optimizer.evaluations} batched evaluations, {dt:.2f} s "

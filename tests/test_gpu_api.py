@@ -307,3 +307,27 @@ def test_user_defined_goal_and_loss_term_run_through_the_cuda_adjoint():
         qo = torch.tensor(scale * q, requires_grad=True)
         go, = torch.autograd.grad(scalar_of(omodel(qo, xp), 0), qo)
         assert np.max(np.abs(qb.grad[b].cpu().numpy() - go.numpy())) < 1e-7 * np.max(np.abs(go.numpy()))
+
+
+def test_ensemble_optimisation_stays_on_the_device_and_sits_behind_minimize():
+    """Optimizer.minimize(q0=q[B, E]) dispatches to the device-resident lock-step L-BFGS: tensors in, tensors out, and the
+    same optima as the NumPy-facing call; the evaluation it uses returns device tensors."""
+    import torch
+    case = CASES["dome"]
+    net = case["network"]
+    model = EquilibriumModel(net)
+    loss = Loss(*goal_objects(case))
+    rng = np.random.default_rng(4)
+    q0 = np.clip(case["q"][None, :] * (1.0 + 0.2 * (rng.random((24, len(case["q"]))) - 0.5)), -50.0, -1e-3)
+    f_dev, g_dev = loss.value_and_grad_device(torch.as_tensor(q0, device="cuda"), model)
+    f_host, g_host = loss.value_and_grad(q0, model)
+    assert f_dev.is_cuda and g_dev.is_cuda and np.allclose(f_dev.cpu().numpy(), f_host, rtol=1e-12) and np.allclose(g_dev.cpu().numpy(), g_host, rtol=1e-9, atol=1e-12)
+    opt = SLSQP(disp=False)
+    q_np = opt.minimize(net, loss, bounds=(-50.0, -1e-3), maxiter=40, tol=1e-7, verbose=False, q0=q0)
+    assert isinstance(q_np, np.ndarray) and q_np.shape == q0.shape and opt.result["nit"] > 0
+    q_t = BFGS(disp=False).minimize(net, loss, bounds=(-50.0, -1e-3), maxiter=40, tol=1e-7, verbose=False, q0=torch.as_tensor(q0, device="cuda"))
+    assert isinstance(q_t, torch.Tensor) and q_t.is_cuda
+    assert np.allclose(q_t.cpu().numpy(), q_np, rtol=1e-9, atol=1e-12)          # the same iteration, whatever the container
+    end = loss(q_np, model)
+    assert np.all(end <= f_host + 1e-12) and end.mean() < 0.5 * f_host.mean()
+    assert np.all(q_np <= -1e-3) and np.all(q_np >= -50.0)
