@@ -236,9 +236,13 @@ static int arena_prepare(Plan::Arena& a, int64_t bytes) {
 // How a host call splits its batch: the copies of chunk k+1 (in) and chunk k-1 (out) run under the kernels of chunk k,
 // so only the first chunk's way in and the last chunk's way out are exposed.  Chunks are multiples of 32 designs where
 // the batch allows, so every chunk keeps whole warps of design lanes.  DFDM_HOST_CHUNKS overrides the count (tuning).
-static int host_chunks(int B, bool pcg, int* b0 /* [kHostChunksMax + 1] */) {
+static int host_chunks(int B, bool pcg, int64_t bytes_per_design, int* b0 /* [kHostChunksMax + 1] */) {
+    // Measured (profiles/README.md, round 2): on the PCG path a batch cut in two evaluates 26 % slower than whole (its
+    // small multigrid levels are latency bound and do not shrink with the batch), far more than the hidden copies return,
+    // so PCG calls stay whole.  The direct path is one kernel per chunk with no host polling: cutting pays once a chunk's
+    // copies outweigh a launch (>= 32 MB of q per chunk).
     static const int forced = std::getenv("DFDM_HOST_CHUNKS") ? std::atoi(std::getenv("DFDM_HOST_CHUNKS")) : 0;
-    int k = forced > 0 ? forced : (pcg ? (B >= 128 ? 2 : 1) : (B >= 512 ? 4 : 1));
+    int k = forced > 0 ? forced : (pcg ? 1 : (int)std::min<int64_t>(4, ((int64_t)B * bytes_per_design) / (32ll << 20)));
     k = std::max(1, std::min(std::min(k, Plan::kHostChunksMax), B));
     const int unit = B >= 64 * k ? 32 : (B >= 4 * k ? 2 : 1);
     const int units = (B + unit - 1) / unit;
@@ -452,7 +456,7 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     int rc = resolve_solver(*plan, options, solver);
     if (rc) return rc;
     int cb[Plan::kHostChunksMax + 1];
-    const int nchunks = host_chunks(B, solver == DFDM_SOLVER_PCG, cb);
+    const int nchunks = host_chunks(B, solver == DFDM_SOLVER_PCG, 8 * E, cb);
     int widest = 0;
     for (int c = 0; c < nchunks; ++c) widest = std::max(widest, cb[c + 1] - cb[c]);
     int64_t ws_bytes = dfdm_workspace_bytes(plan, widest, options);

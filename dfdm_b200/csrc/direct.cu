@@ -13,6 +13,21 @@
 //                                 lcol[w+1], lsc[w+1]  column scratch of the factorisation
 // LDL^T needs no sign handling: K is negative definite for compression (q < 0), positive definite
 // for tension, and merely needs non-zero pivots when q has mixed sign.
+//
+// Two launch shapes share the per-design body (eval_design):
+//   k_direct_eval  one CTA per design, column-by-column LDL^T with block barriers: wide bands (w > 28), long chains
+//                  (w = 1) and designs whose factor takes most of a CTA's shared memory
+//   k_direct_warp  one WARP per design, several designs per CTA, for 2 <= w <= 28: nothing but __syncwarp between the
+//                  stages; the factorisation is BLOCKED by four columns - the panel of a block is eliminated in
+//                  registers (a lane per row, pivots and multipliers by shuffle) and the trailing window takes the
+//                  block's rank-4 update as FP64 tensor-core products (mma.sync.m8n8k4.f64, operands read straight from
+//                  the band) - and the substitutions keep the three right-hand sides in registers, a 64-row sliding
+//                  window over the lanes, so a column costs a shuffle and a multiply-add instead of a shared-memory trip.
+// After the forward solve both check the residual of the solve itself (R on the free nodes, which is computed anyway)
+// against the terms it is a difference of: an unpivoted factorisation of an indefinite K can lose accuracy through a tiny
+// pivot without ever hitting an exact zero, and must not report DFDM_STATUS_OK then.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dfdm {
@@ -26,8 +41,13 @@ struct DirectArgs {
     const double* q;
     const double* loads;
     const double* xfix;
-    double *X, *R, *U, *L, *F;       // [B][..] design-major state (caller's outputs or workspace)
-    double *Rb, *Xb, *Ub;            // cotangent scratch
+    double *X, *R, *U, *L, *F;       // [B][..] design-major state in global memory (workspace; unused when the state is in shared memory)
+    double *Rb, *Xb, *Ub;            // cotangent scratch, likewise
+    double *oX, *oR, *oU, *oL, *oF;  // the caller's outputs (nullable)
+    int chain_off;                   // >= 0 (w = 1 only): scratch of the partition method at this offset (doubles); -1: the serial sweeps
+    int state_off;                   // >= 0: the per-design state lives in shared memory, at this offset (doubles) of the group's block:
+                                     // q[E], X[3n] (later Xbar), U[3E], L[E], F[E], Rbar[3n], Ubar[3E] - every pass then runs on shared
+                                     // memory and only q comes in and loss / dq (and requested outputs) go out
     const double *c_xyz, *c_res, *c_vec, *c_len, *c_for;
     double* loss;
     double* dq;
@@ -47,6 +67,20 @@ __device__ double cta_sum(double v, double* red, int nt) {
     __syncthreads();
     double s = 0.0;
     for (int k = 0; k < (nt >> 5); ++k) s += red[k];   // fixed order: deterministic
+    return s;
+}
+
+constexpr double kDirectResidualTol = 1e-9;     // largest |R| on a free node, relative to the largest term of any nodal balance
+
+__device__ double cta_max(double v, double* red, int nt) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (nt <= 32) return __shfl_sync(0xffffffffu, v, 0);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int k = 0; k < (nt >> 5); ++k) s = fmax(s, red[k]);
     return s;
 }
 
@@ -118,27 +152,355 @@ __device__ void band_solve(const double* __restrict__ D, double* __restrict__ rh
     }
 }
 
-__global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
-    extern __shared__ double smem[];
+// ---- chains (w = 1): partition method ------------------------------------------------------------------------------------
+// K is tridiagonal.  The classic recurrences (d_i = a_i - b_i^2 / d_(i-1), one substitution step per row) are n_f
+// DEPENDENT steps - 25 000 for the factorisation and the two solves of a 5 000-segment arch.  Instead the chain is cut
+// into C <= 256 parts of m rows (m odd: conflict-free strides); the last row of every part but the last is an INTERFACE.
+// Every part's interior is an independent tridiagonal block T_c that ONE thread factors and solves on its own (m
+// dependent steps, all parts at once); the interfaces see each other through the Schur complement
+//     S = A_II - B T^-1 B^T,   tridiagonal of order C - 1,
+// whose entries need only (T_c^-1)_first,first = sum_i y_i^2 / d_i, (T_c^-1)_last,last = 1 / d_last and
+// (T_c^-1)_first,last = y_last / d_last (y: the unit-lower recurrence started at e_first), and which is solved by parallel
+// cyclic reduction, one thread per interface, log2(C) steps.  A solve is: one store-free sweep per part for the two end
+// values of T_c^-1 r_c, the reduced system, then the interior solves with the interface values moved to the right-hand
+// side.  Storage: the band in place (1 / d on the diagonal of interior rows, multipliers on the sub-diagonal; interface
+// rows keep a and b) plus 11 arrays of 256 doubles.
+constexpr int kChainParts = 256;
+constexpr int kChainScratch = 11 * kChainParts;          // doubles
+
+struct ChainGeom { int m, C; };
+__host__ __device__ inline ChainGeom chain_geom(int nf) {
+    ChainGeom g;
+    g.m = max(3, ((nf + kChainParts - 1) / kChainParts) | 1);
+    g.C = (nf + g.m - 1) / g.m;
+    return g;
+}
+
+// returns non-zero (in every thread of the CTA) on a zero / non-finite pivot
+__device__ int chain_factor(double* __restrict__ D, int nf, int LD, double* __restrict__ scr, int* s_flag) {
+    const ChainGeom g = chain_geom(nf);
+    const int c = threadIdx.x;
+    double *alpha = scr, *beta = scr + kChainParts, *gamma = scr + 2 * kChainParts, *sd = scr + 3 * kChainParts, *so = scr + 4 * kChainParts;
+    int bad = 0;
+    if (c < g.C) {
+        const int s = c * g.m, e = min(nf, s + g.m), t = c < g.C - 1 ? e - 1 : e;
+        double d = D[s];
+        if (d == 0.0 || !isfinite(d)) bad = 1;
+        double rd = 1.0 / d, y = 1.0, al = rd;
+        D[s] = rd;
+        for (int i = s + 1; i < t; ++i) {
+            const double b = D[LD + i];
+            const double l = b * rd;
+            d = D[i] - l * b;
+            if (d == 0.0 || !isfinite(d)) bad = 1;
+            rd = 1.0 / d;
+            D[LD + i] = l;
+            D[i] = rd;
+            y = -l * y;
+            al += y * y * rd;
+        }
+        alpha[c] = al;
+        beta[c] = rd;
+        gamma[c] = y * rd;
+    }
+    if (bad) *s_flag = 1;
+    __syncthreads();
+    if (c < g.C - 1) {
+        const int I = min(nf, (c + 1) * g.m) - 1;
+        const double bl = D[LD + I], br = D[LD + I + 1];
+        sd[c] = D[I] - bl * bl * beta[c] - br * br * alpha[c + 1];
+        double off = 0.0;
+        if (c + 1 < g.C - 1) {
+            const int I2 = min(nf, (c + 2) * g.m) - 1;
+            off = -br * gamma[c + 1] * D[LD + I2];
+        }
+        so[c] = off;
+    }
+    __syncthreads();
+    return *s_flag;
+}
+
+__device__ void chain_solve(const double* __restrict__ D, double* __restrict__ rhs, int nf, int LD, double* __restrict__ scr) {
+    const ChainGeom g = chain_geom(nf);
+    const int c = threadIdx.x, N = g.C - 1;
+    double *yf = scr, *sd = scr + 3 * kChainParts, *so = scr + 4 * kChainParts;          // yf[3][parts] takes the place of alpha / beta / gamma
+    double *pa = scr + 5 * kChainParts, *pd = scr + 6 * kChainParts, *pc = scr + 7 * kChainParts, *pr = scr + 8 * kChainParts;
+    const int s = c * g.m, e = min(nf, s + g.m), t = c < g.C - 1 ? e - 1 : e;
+    double yl[3] = {0.0, 0.0, 0.0};
+    if (c < g.C) {
+        // end values of T^-1 r for this part, no stores: x_last = z_last, x_first = sum_i y_i z_i
+        double v[3], xf[3];
+        const double rd0 = D[s];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[k] = rhs[k * nf + s]; xf[k] = v[k] * rd0; }
+        double y = 1.0, rd = rd0;
+        for (int i = s + 1; i < t; ++i) {
+            const double l = D[LD + i];
+            rd = D[i];
+            y = -l * y;
+            const double yr = y * rd;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v[k] = rhs[k * nf + i] - l * v[k]; xf[k] += yr * v[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { yl[k] = v[k] * rd; yf[k * kChainParts + c] = xf[k]; }
+    }
+    __syncthreads();
+    // reduced system on the interfaces: parallel cyclic reduction, own coefficients in registers
+    double a = 0.0, d = 1.0, cc = 0.0, r[3] = {0.0, 0.0, 0.0};
+    const int I = min(nf, (c + 1) * g.m) - 1;
+    if (c < N) {
+        const double bl = D[LD + I], br = D[LD + I + 1];
+        a = c > 0 ? so[c - 1] : 0.0;
+        d = sd[c];
+        cc = so[c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) r[k] = rhs[k * nf + I] - bl * yl[k] - br * yf[k * kChainParts + c + 1];
+    }
+    for (int h = 1; h < N; h <<= 1) {
+        __syncthreads();
+        if (c < N) { pa[c] = a; pd[c] = d; pc[c] = cc; pr[c] = r[0]; pr[kChainParts + c] = r[1]; pr[2 * kChainParts + c] = r[2]; }
+        __syncthreads();
+        if (c < N) {
+            const int lo = c - h, hi = c + h;
+            double k1 = 0.0, k2 = 0.0, na = 0.0, nc = 0.0;
+            if (lo >= 0) {
+                k1 = a / pd[lo];
+                na = -k1 * pa[lo];
+                d -= k1 * pc[lo];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r[k] -= k1 * pr[k * kChainParts + lo];
+            }
+            if (hi < N) {
+                k2 = cc / pd[hi];
+                nc = -k2 * pc[hi];
+                d -= k2 * pa[hi];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r[k] -= k2 * pr[k * kChainParts + hi];
+            }
+            a = na;
+            cc = nc;
+        }
+    }
+    if (c < N) {
+        const double rd = 1.0 / d;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rhs[k * nf + I] = r[k] * rd;
+    }
+    __syncthreads();
+    // interiors, with the interface values on the right-hand side
+    if (c < g.C) {
+        const double bs = c > 0 ? D[LD + s] : 0.0, bt = c < g.C - 1 ? D[LD + t] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double* x = rhs + (size_t)k * nf;
+            const double xl = c > 0 ? x[s - 1] : 0.0, xr = c < g.C - 1 ? x[t] : 0.0;
+            x[s] -= bs * xl;
+            x[t - 1] -= bt * xr;
+            double v = x[s];
+            x[s] = v * D[s];
+            for (int i = s + 1; i < t; ++i) {
+                v = x[i] - D[LD + i] * v;
+                x[i] = v * D[i];                              // z = y / d
+            }
+            double xn = x[t - 1];
+            for (int i = t - 2; i >= s; --i) {
+                xn = x[i] - D[LD + i + 1] * xn;
+                x[i] = xn;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- warp-per-design building blocks (2 <= w <= kWarpMaxW) ------------------------------------------------------------
+
+constexpr int kWarpMaxW = 28;            // a block's panel has w + 4 rows: one lane each
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Banded LDL^T of one design by one warp, blocked by four columns.  D[k * LD + i] = K(i, i - k) on entry; on exit the
+// diagonal holds d and the sub-diagonals the unit-lower multipliers.  Returns non-zero (in every lane) on a zero or
+// non-finite pivot.
+__device__ int band_ldlt_warp(double* __restrict__ D, int nf, int w, int LD) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;                    // mma fragment coordinates
+    int bad = 0;
+    for (int j0 = 0; j0 < nf; j0 += 4) {
+        const int nb = min(4, nf - j0);
+        const int row = j0 + lane;
+        // ---- the panel: rows j0 .. j0 + w + 3, columns j0 .. j0 + nb - 1, a lane per row, in registers ----------------
+        double p[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool in = c < nb && c <= lane && lane - c <= w && row < nf;
+            p[c] = in ? D[(lane - c) * LD + row] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c >= nb) break;
+            const double piv = __shfl_sync(kFull, p[c], c);   // lane c holds the diagonal entry of column j0 + c
+            if (piv == 0.0 || !isfinite(piv)) bad = 1;
+            const double rinv = 1.0 / piv;
+            const double v = lane > c ? p[c] : 0.0;           // l d of this row (zero above the diagonal and outside the band)
+            const double l = v * rinv;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 4; ++c2) {
+                const double lc2 = __shfl_sync(kFull, l, c2); // multiplier of row j0 + c2 in column j0 + c
+                if (c2 < nb && lane >= c2) p[c2] -= v * lc2;
+            }
+            if (lane > c) p[c] = l;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool in = c < nb && c <= lane && lane - c <= w && row < nf;
+            if (in) D[(lane - c) * LD + row] = p[c];
+        }
+        __syncwarp();
+        // ---- the trailing window (rows and columns j0 + 4 .. j0 + 3 + w) takes the rank-4 update on the tensor cores ----
+        const int W0 = j0 + 4;
+        const int count = min(w, nf - W0);
+        if (nb == 4 && count > 0) {
+            const double dk = D[j0 + t];                      // pivot of this lane's k index
+            const int tiles = (count + 7) >> 3;
+            for (int ti = 0; ti < tiles; ++ti) {
+                const int ra = W0 + 8 * ti + g;               // A fragment: row ra, column j0 + t, scaled by -d
+                const int ka = ra - (j0 + t);
+                const double af = (ra < nf && ka <= w) ? -D[ka * LD + ra] * dk : 0.0;
+                for (int tj = 0; tj <= ti; ++tj) {
+                    const int cb = W0 + 8 * tj + g;           // B fragment: k = t, column cb of the window = row cb of the panel
+                    const int kb = cb - (j0 + t);
+                    const double bf = (cb < nf && kb <= w) ? D[kb * LD + cb] : 0.0;
+                    const int rc = W0 + 8 * ti + g, cc = W0 + 8 * tj + 2 * t;
+                    const bool in0 = rc < nf && cc <= rc && rc - cc <= w, in1 = rc < nf && cc + 1 <= rc && rc - cc - 1 <= w;
+                    double c0 = in0 ? D[(rc - cc) * LD + rc] : 0.0, c1 = in1 ? D[(rc - cc - 1) * LD + rc] : 0.0;
+                    dmma_884(c0, c1, af, bf);
+                    if (in0) D[(rc - cc) * LD + rc] = c0;
+                    if (in1) D[(rc - cc - 1) * LD + rc] = c1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    return __any_sync(kFull, bad);
+}
+
+// (L D L^T) x = rhs for the three columns, one warp: the rows travel through registers in two 32-row slots (the current
+// one and its neighbour), a lane per row; a column costs one shuffle per right-hand side and a multiply-add - no branch
+// (every lane updates exactly one row per column, in one slot or the other: the multiplier is routed by a select) and
+// the multiplier of the next column is in flight while this column's chain (shuffle -> multiply-add) completes.
+__device__ void band_solve_warp(const double* __restrict__ D, double* __restrict__ rhs, int nf, int w, int LD) {
+    const int lane = threadIdx.x & 31;
+    const int nslots = (nf + 31) >> 5;
+    double cur[3], nxt[3];
+    // ---- forward: L y = b, then z = y / d on the way out of the registers -----------------------------------------
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cur[c] = lane < nf ? rhs[c * nf + lane] : 0.0;
+    for (int s = 0; s < nslots; ++s) {
+        const int r0 = 32 * s + lane, r1 = r0 + 32;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nxt[c] = r1 < nf ? rhs[c * nf + r1] : 0.0;
+        const int jmax = min(32, nf - 32 * s);
+        // multiplier of this lane's row for column lj: l(row, 32 s + lj); row in the current slot when lane > lj
+        auto mult = [&](int lj) {
+            const bool own = lane > lj;
+            const int k = own ? lane - lj : lane - lj + 32, row = own ? r0 : r1;
+            return (lj < jmax && k <= w && row < nf) ? D[k * LD + row] : 0.0;
+        };
+        double l = mult(0);
+        for (int lj = 0; lj < jmax; ++lj) {
+            const double ln = mult(lj + 1);                     // next column's multiplier: independent of the chain
+            const double y0 = __shfl_sync(kFull, cur[0], lj), y1 = __shfl_sync(kFull, cur[1], lj), y2 = __shfl_sync(kFull, cur[2], lj);
+            const double lo = lane > lj ? l : 0.0, lx = lane > lj ? 0.0 : l;
+            cur[0] -= lo * y0; cur[1] -= lo * y1; cur[2] -= lo * y2;
+            nxt[0] -= lx * y0; nxt[1] -= lx * y1; nxt[2] -= lx * y2;
+            l = ln;
+        }
+        if (r0 < nf) {
+            const double dinv = 1.0 / D[r0];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rhs[c * nf + r0] = cur[c] * dinv;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cur[c] = nxt[c];
+    }
+    __syncwarp();
+    // ---- backward: L^T x = z, slots from the last to the first; `nxt` now holds the slot BELOW the current one ----------
+    {
+        const int rl = 32 * (nslots - 1) + lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cur[c] = rl < nf ? rhs[c * nf + rl] : 0.0;
+    }
+    for (int s = nslots - 1; s >= 0; --s) {
+        const int r0 = 32 * s + lane, rp = r0 - 32;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nxt[c] = s > 0 ? rhs[c * nf + rp] : 0.0;
+        const int jtop = min(32, nf - 32 * s) - 1;
+        // multiplier l(j, row) of column j = 32 s + lj for this lane's row: j - k, in the current slot when lane < lj
+        auto mult = [&](int lj) {
+            const bool own = lane < lj;
+            const int k = own ? lj - lane : lj - lane + 32;
+            return (lj >= 0 && k <= w && (own || s > 0)) ? D[k * LD + 32 * s + lj] : 0.0;
+        };
+        double l = mult(jtop);
+        for (int lj = jtop; lj >= 0; --lj) {
+            const double ln = mult(lj - 1);
+            const double x0 = __shfl_sync(kFull, cur[0], lj), x1 = __shfl_sync(kFull, cur[1], lj), x2 = __shfl_sync(kFull, cur[2], lj);
+            const double lo = lane < lj ? l : 0.0, lx = lane < lj ? 0.0 : l;
+            cur[0] -= lo * x0; cur[1] -= lo * x1; cur[2] -= lo * x2;
+            nxt[0] -= lx * x0; nxt[1] -= lx * x1; nxt[2] -= lx * x2;
+            l = ln;
+        }
+        if (r0 < nf) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rhs[c * nf + r0] = cur[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cur[c] = nxt[c];
+    }
+    __syncwarp();
+}
+
+// leading dimension of the band: odd for the CTA kernel (its trailing update walks band rows); for the warp kernel
+// LD = 2 (mod 4), so that a lane-per-row walk (stride LD + 1, odd) is conflict free and a lane-per-offset walk (stride LD)
+// meets two-way conflicts at most
+__host__ __device__ inline int direct_ld(int nf, bool warp) { return warp ? ((nf + 1) & ~3) + 2 : (nf | 1); }
+
+// One design, start to finish, by the `nt` threads of a group (a whole CTA, or one warp of it when WARP): tid = index in
+// the group, smem = the group's shared memory.
+template <bool WARP>
+__device__ void eval_design(const DirectArgs& a, const int b, double* smem, const int tid, const int nt, int* s_bad) {
     const PlanDev& P = a.P;
     const int nf = P.nf, n = P.n, E = P.E, w = P.w;
-    const int LD = nf | 1;
-    const int nt = blockDim.x, tid = threadIdx.x;
+    const int LD = direct_ld(nf, WARP);
     double* D = smem;
     double* rhs = D + (size_t)(w + 1) * LD;
-    double* lcol = rhs + 3 * (size_t)nf;
+    double* lcol = rhs + 3 * (size_t)nf;         // CTA kernel only
     double* lsc = lcol + (w + 1);
     double* red = lsc + (w + 1);                 // 16 doubles
-    __shared__ int s_bad;
-
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    int bad_w = 0;                               // warp kernel: the verdict lives in registers
+    {
+        const bool in_smem = a.state_off >= 0;
+        double* st = smem + (in_smem ? a.state_off : 0);
         const double* q = a.q + (size_t)b * E;
-        double* X = a.X + (size_t)b * n * 3;
-        double* U = a.U + (size_t)b * E * 3;
-        double* Lg = a.L + (size_t)b * E;
-        double* F = a.F + (size_t)b * E;
-        double* R = a.R + (size_t)b * n * 3;
-        if (tid == 0) s_bad = 0;
+        double* X = in_smem ? st + E : a.X + (size_t)b * n * 3;
+        double* U = in_smem ? X + 3 * (size_t)n : a.U + (size_t)b * E * 3;
+        double* Lg = in_smem ? U + 3 * (size_t)E : a.L + (size_t)b * E;
+        double* F = in_smem ? Lg + E : a.F + (size_t)b * E;
+        double* oX = a.oX ? a.oX + (size_t)b * n * 3 : nullptr;
+        double* oR = a.oR ? a.oR + (size_t)b * n * 3 : nullptr;
+        double* oU = a.oU ? a.oU + (size_t)b * E * 3 : nullptr;
+        double* oL = a.oL ? a.oL + (size_t)b * E : nullptr;
+        double* oF = a.oF ? a.oF + (size_t)b * E : nullptr;
+        if (!WARP && tid == 0) *s_bad = 0;
+        if (in_smem) {                               // q is read by five passes: once from global memory
+            for (int e = tid; e < E; e += nt) st[e] = q[e];
+            q = st;
+            cta_sync(nt);
+        }
 
         // ---- assembly: gather form of the scatter-add, one segment (row) per thread ----------------
         for (int idx = tid; idx < (w + 1) * LD; idx += nt) D[idx] = 0.0;
@@ -168,7 +530,11 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
         cta_sync(nt);
 
         // ---- banded LDL^T, right-looking, in place ---------------------------------------------------
-        if (w == 1) {
+        if (WARP) {
+            bad_w = band_ldlt_warp(D, nf, w, LD);
+        } else if (w == 1 && a.chain_off >= 0) {
+            chain_factor(D, nf, LD, smem + a.chain_off, s_bad);
+        } else if (w == 1) {
             // chains: d_(j+1) = K(j+1,j+1) - l^2 d_j with l = K(j+1,j) / d_j is one division and one multiply-add per row,
             // strictly sequential; one thread runs it without the two barriers per column of the general path
             if (tid == 0) {
@@ -186,7 +552,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
                     D[j + 1] = d;
                     if (d == 0.0 || !isfinite(d)) bad = 1;
                 }
-                if (bad) s_bad = 1;
+                if (bad) *s_bad = 1;
             }
             cta_sync(nt);
         } else {
@@ -194,7 +560,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
             for (int j = 0; j < nf - 1; ++j) {
                 int m = min(w, nf - 1 - j);
                 double dj = D[j];
-                if (tid == 0 && (dj == 0.0 || !isfinite(dj))) s_bad = 1;
+                if (tid == 0 && (dj == 0.0 || !isfinite(dj))) *s_bad = 1;
                 for (int k = 1 + tid; k <= m; k += nt) {
                     double v = D[k * LD + j + k];
                     lcol[k] = v;                 // l_k d_j
@@ -210,25 +576,26 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
             }
             if (tid == 0) {
                 double dl = D[nf - 1];
-                if (dl == 0.0 || !isfinite(dl)) s_bad = 1;
+                if (dl == 0.0 || !isfinite(dl)) *s_bad = 1;
             }
         }
 
         // ---- forward solve and equilibrium state ------------------------------------------------------
-        band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
+        if (WARP) band_solve_warp(D, rhs, nf, w, LD);
+        else if (w == 1 && a.chain_off >= 0) chain_solve(D, rhs, nf, LD, smem + a.chain_off);
+        else band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
         for (int i = tid; i < n; i += nt) {
             int src = P.node_src[i];
+            double x0, x1, x2;
             if (src >= 0) {
                 int p = P.pos[src];
-                X[i * 3 + 0] = rhs[p];
-                X[i * 3 + 1] = rhs[nf + p];
-                X[i * 3 + 2] = rhs[2 * nf + p];
+                x0 = rhs[p]; x1 = rhs[nf + p]; x2 = rhs[2 * nf + p];
             } else {
                 const double* xk = a.xfix + (size_t)(-1 - src) * 3;
-                X[i * 3 + 0] = xk[0];
-                X[i * 3 + 1] = xk[1];
-                X[i * 3 + 2] = xk[2];
+                x0 = xk[0]; x1 = xk[1]; x2 = xk[2];
             }
+            X[i * 3 + 0] = x0; X[i * 3 + 1] = x1; X[i * 3 + 2] = x2;
+            if (oX) { oX[i * 3 + 0] = x0; oX[i * 3 + 1] = x1; oX[i * 3 + 2] = x2; }
         }
         cta_sync(nt);
         double lp_part = 0.0;
@@ -242,26 +609,34 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
             U[e * 3 + 2] = u2;
             Lg[e] = len;
             F[e] = f;
+            if (oU) { oU[e * 3 + 0] = u0; oU[e * 3 + 1] = u1; oU[e * 3 + 2] = u2; }
+            if (oL) oL[e] = len;
+            if (oF) oF[e] = f;
             lp_part += fabs(len * f);
         }
         cta_sync(nt);
 
         double loss_part = 0.0;
         const bool seeds = a.adjoint;
-        double* Rb = seeds ? a.Rb + (size_t)b * n * 3 : nullptr;
-        double* Xb = seeds ? a.Xb + (size_t)b * n * 3 : nullptr;
+        // cotangents: in shared memory Xbar takes the place of X (a node's position is read by its own thread only, before it
+        // writes Xbar of the same node)
+        double* Rb = !seeds ? nullptr : (in_smem ? F + E : a.Rb + (size_t)b * n * 3);
+        double* Xb = !seeds ? nullptr : (in_smem ? X : a.Xb + (size_t)b * n * 3);
+        double res_max = 0.0, term_max = 0.0;        // residual of the solve on the free nodes against the size of its terms
         for (int i = tid; i < n; i += nt) {
             double r[3] = {a.loads[i * 3 + 0], a.loads[i * 3 + 1], a.loads[i * 3 + 2]};
+            double terms = fmax(fabs(r[0]), fmax(fabs(r[1]), fabs(r[2])));
             for (int k = P.ninc_ptr[i]; k < P.ninc_ptr[i + 1]; ++k) {
                 int e = P.ninc_edge[k];
                 double s = (double)P.ninc_sign[k] * q[e];
                 r[0] -= s * U[e * 3 + 0];
                 r[1] -= s * U[e * 3 + 1];
                 r[2] -= s * U[e * 3 + 2];
+                terms = fmax(terms, fabs(s) * fmax(fabs(U[e * 3 + 0]), fmax(fabs(U[e * 3 + 1]), fabs(U[e * 3 + 2]))));
             }
-            R[i * 3 + 0] = r[0];
-            R[i * 3 + 1] = r[1];
-            R[i * 3 + 2] = r[2];
+            term_max = fmax(term_max, terms);
+            if (P.node_src[i] >= 0) res_max = fmax(res_max, fmax(fabs(r[0]), fmax(fabs(r[1]), fabs(r[2]))));
+            if (oR) { oR[i * 3 + 0] = r[0]; oR[i * 3 + 1] = r[1]; oR[i * 3 + 2] = r[2]; }     // R is consumed here: stored only on request
             if (a.has_prog || seeds) {
                 double xb[3] = {0.0, 0.0, 0.0}, rb[3] = {0.0, 0.0, 0.0};
                 if (a.has_prog) {
@@ -286,7 +661,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
         cta_sync(nt);
 
         // ---- reverse pass ------------------------------------------------------------------------------
-        double* Ub = seeds ? a.Ub + (size_t)b * E * 3 : nullptr;
+        double* Ub = !seeds ? nullptr : (in_smem ? F + E + 3 * (size_t)n : a.Ub + (size_t)b * E * 3);
         double* dq = seeds ? a.dq + (size_t)b * E : nullptr;
         if (a.has_prog || seeds) {
             for (int e = tid; e < E; e += nt) {
@@ -335,7 +710,9 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
                 rhs[2 * nf + p] = xb[2];
             }
             cta_sync(nt);
-            band_solve(D, rhs, nf, w, LD, nt, a.k_shift);       // K symmetric: same factor
+            if (WARP) band_solve_warp(D, rhs, nf, w, LD);                                           // K symmetric: same factor
+            else if (w == 1 && a.chain_off >= 0) chain_solve(D, rhs, nf, LD, smem + a.chain_off);
+            else band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
             for (int e = tid; e < E; e += nt) {
                 int su = P.node_src[P.edges[2 * e]], sv = P.node_src[P.edges[2 * e + 1]];
                 double d = 0.0;
@@ -348,9 +725,36 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
             }
         }
         cta_sync(nt);
-        if (tid == 0 && a.status) a.status[b] = s_bad ? DFDM_STATUS_SINGULAR : DFDM_STATUS_OK;
+        // verdict: a zero / non-finite pivot, or a solve whose own residual is not small against its terms (tiny pivots of an
+        // indefinite K: the answer would be inaccurate with every pivot non-zero).  Both map to LinAlgError on the host.
+        const double rmax = cta_max(res_max, red, nt), tmax = cta_max(term_max, red, nt);
+        const bool inaccurate = !(rmax <= kDirectResidualTol * tmax);
+        const int bad = WARP ? bad_w : *s_bad;
+        if (tid == 0 && a.status) a.status[b] = (bad || inaccurate) ? DFDM_STATUS_SINGULAR : DFDM_STATUS_OK;
         cta_sync(nt);
     }
+}
+
+__global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
+    extern __shared__ double smem[];
+    __shared__ int s_bad;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<false>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+}
+
+// the same body for long chains: 1 024 threads (64 registers) - the partition solver is light, the node / edge passes over
+// thousands of elements want the threads
+__global__ void __launch_bounds__(1024) k_direct_chain(DirectArgs a) {
+    extern __shared__ double smem[];
+    __shared__ int s_bad;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<false>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+}
+
+// one warp per design; `stride` doubles of shared memory per warp
+__global__ void __launch_bounds__(256) k_direct_warp(DirectArgs a, int stride) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    double* mine = smem + (size_t)warp * stride;
+    for (int b = blockIdx.x * warps + warp; b < a.B; b += gridDim.x * warps) eval_design<true>(a, b, mine, threadIdx.x & 31, 32, nullptr);
 }
 
 int64_t direct_workspace(const Plan& P, int B, bool adjoint, bool has_prog) {
@@ -383,16 +787,14 @@ int run_direct(Eval& ev) {
     a.q = ev.q;
     a.loads = ev.loads;
     a.xfix = ev.xfix;
-    double* wX = bump.take<double>(B * n * 3);
-    double* wR = bump.take<double>(B * n * 3);
-    double* wU = bump.take<double>(B * E * 3);
-    double* wL = bump.take<double>(B * E);
-    double* wF = bump.take<double>(B * E);
-    a.X = ev.o_xyz ? ev.o_xyz : wX;
-    a.R = ev.o_res ? ev.o_res : wR;
-    a.U = ev.o_vec ? ev.o_vec : wU;
-    a.L = ev.o_len ? ev.o_len : wL;
-    a.F = ev.o_for ? ev.o_for : wF;
+    a.X = bump.take<double>(B * n * 3);
+    a.R = bump.take<double>(B * n * 3);
+    a.U = bump.take<double>(B * E * 3);
+    a.L = bump.take<double>(B * E);
+    a.F = bump.take<double>(B * E);
+    a.oX = ev.o_xyz; a.oR = ev.o_res; a.oU = ev.o_vec; a.oL = ev.o_len; a.oF = ev.o_for;
+    a.state_off = -1;
+    a.chain_off = -1;
     if (ev.adjoint) {
         a.Rb = bump.take<double>(B * n * 3);
         a.Xb = bump.take<double>(B * n * 3);
@@ -412,8 +814,42 @@ int run_direct(Eval& ev) {
     a.status = ev.status;
 
     const int w = P.w;
+    int dev = 0, sms = 0, per_sm = 0;
+    DFDM_CUDA_OK(cudaGetDevice(&dev));
+    DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // ---- one warp per design: narrow bands whose factor leaves room for several designs per SM ------------------------
+    static const bool warp_off = std::getenv("DFDM_DIRECT_WARP") && std::atoi(std::getenv("DFDM_DIRECT_WARP")) == 0;
+    const int64_t factor_part = (int64_t)(w + 1) * direct_ld(P.nf, true) + 3 * (int64_t)P.nf + 2 * (int64_t)(w + 1) + 16;   // doubles
+    const int64_t state_part = 6 * n + 9 * E;                  // q, X / Xbar, U, L, F, Rbar, Ubar
+    const int64_t per_design = factor_part + state_part;
+    if (!warp_off && w >= 2 && w <= kWarpMaxW && per_design * 8 <= 100 * 1024) {
+        a.state_off = (int)factor_part;
+        // designs per CTA: up to 8 warps, as many as fit ~100 KB so that two CTAs share an SM; fewer when the batch is small
+        int warps = (int)std::max<int64_t>(1, std::min<int64_t>(8, (100 * 1024) / (per_design * 8)));
+        while (warps > 1 && (B + warps - 1) / warps < sms) warps >>= 1;      // spread a small batch over the SMs first
+        const size_t smem = (size_t)warps * per_design * 8;
+        if (smem > 48 * 1024) {
+            static std::mutex mu;
+            static std::map<int, size_t> configured;
+            std::lock_guard<std::mutex> lock(mu);
+            if (configured[dev] < smem) {
+                DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = smem;
+            }
+        }
+        DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_warp, warps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int64_t ctas = (B + warps - 1) / warps;
+        const int grid = (int)std::min<int64_t>(ctas, (int64_t)sms * per_sm);
+        k_direct_warp<<<grid, warps * 32, smem, ev.stream>>>(a, (int)per_design);
+        DFDM_LAUNCH_OK("k_direct_warp");
+        return DFDM_OK;
+    }
     int nt = w <= 6 ? 32 : (w <= 12 ? 64 : (w <= 48 ? 128 : 256));
-    if (w == 1 && P.nf > 256) nt = 256;      // chains: the sweeps are single-threaded anyway, the node / edge passes want the threads
+    static const bool chain_off = std::getenv("DFDM_DIRECT_CHAIN") && std::atoi(std::getenv("DFDM_DIRECT_CHAIN")) == 0;
+    const bool chain = w == 1 && P.nf >= 6 && !chain_off;   // partition method: parts of >= 3 rows, at most 256 of them
+    if (w == 1 && P.nf > 256) nt = 256;
+    if (chain) nt = P.nf > 1024 ? 1024 : 256;               // one thread per part in the solver; the node / edge passes want the threads
     int tx = 4;
     while (tx < 32 && tx < w) tx <<= 1;
     if (tx > nt) tx = nt;
@@ -424,22 +860,29 @@ int run_direct(Eval& ev) {
     while ((1 << kshift) < w) ++kshift;
     a.k_shift = kshift;
     int64_t smem = direct_smem_bytes(P.nf, w);
-    int dev = 0, sms = 0, per_sm = 0;
-    DFDM_CUDA_OK(cudaGetDevice(&dev));
+    if (chain) {
+        a.chain_off = (int)(smem / 8);
+        smem += 8 * (int64_t)kChainScratch;
+    }
+    if (smem + 8 * (6 * n + 9 * E) <= 64 * 1024) {        // small enough to keep the state in shared memory as well
+        a.state_off = (int)(smem / 8);
+        smem += 8 * (6 * n + 9 * E);
+    }
+    auto kernel = nt > 256 ? k_direct_chain : k_direct_eval;
     if (smem > 48 * 1024) {                               // opt-in is per device and per function: set it wherever we launch
         static std::mutex mu;
-        static std::map<int, int64_t> configured;
+        static std::map<std::pair<int, int>, int64_t> configured;
         std::lock_guard<std::mutex> lock(mu);
-        if (configured[dev] < smem) {
-            DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[dev] = smem;
+        int64_t& have = configured[{dev, nt > 256 ? 1 : 0}];
+        if (have < smem) {
+            DFDM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
         }
     }
-    DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_eval, nt, (size_t)smem));
+    DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, (size_t)smem));
     if (per_sm < 1) per_sm = 1;
     int grid = (int)std::min<int64_t>(B, (int64_t)sms * per_sm);
-    k_direct_eval<<<grid, nt, (size_t)smem, ev.stream>>>(a);
+    kernel<<<grid, nt, (size_t)smem, ev.stream>>>(a);
     DFDM_LAUNCH_OK("k_direct_eval");
     return DFDM_OK;
 }

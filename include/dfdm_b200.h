@@ -230,10 +230,12 @@ DFDM_API int dfdm_vjp(const dfdm_plan* plan, int32_t batch,
 /*
  * Host-buffer variants: copy inputs to the current device, evaluate, copy results back, synchronise.
  * Device memory is cached inside the library per (plan, device) and grown on demand.
- * Large batches are pipelined: the batch is cut into chunks of designs (2 on the PCG path from 128 designs on, 4 on the
- * direct path from 512 on); the host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 run on their
- * own streams under the kernels of chunk k, one cudaMemcpyAsync per chunk and array.  Pinned host buffers are needed
- * for the overlap (pageable ones still work, serialised by the driver).
+ * The copies run on streams of their own, chained to the compute stream by events, and the batch can be cut into
+ * chunks of designs whose copies (chunk k+1 in, chunk k-1 out) run under the kernels of chunk k, one cudaMemcpyAsync
+ * per chunk and array: the direct path does so from 32 MB of q per chunk on (at most 4 chunks); the PCG path evaluates
+ * the batch whole (measured: its latency-bound multigrid levels make two half batches 26 % slower than one whole,
+ * more than the hidden copies return; DFDM_HOST_CHUNKS=k forces k chunks for experiments).  Pinned host buffers are
+ * needed for any overlap (pageable ones still work, serialised by the driver).
  */
 DFDM_API int dfdm_forward_host(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
                       double* xyz, double* residuals, double* vectors, double* lengths, double* forces,

@@ -506,3 +506,57 @@ def test_tail_kernel_is_the_same_preconditioner_as_the_launch_per_level_path(nfr
     sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
     loss, dq, st = sm.loss_and_grad_edge_length(q[batch - 1], lengths0, 1.0, 0.1)
     assert _rel(res["tail"][0][batch - 1], st.xyz) < TOL_X and _rel(res["tail"][1][batch - 1], dq) < TOL_G
+
+
+def test_direct_path_flags_a_solve_that_lost_its_accuracy_to_a_tiny_pivot():
+    """Unpivoted LDL^T on an indefinite K: a pivot that is tiny but not zero passes the zero-pivot test and wrecks the
+    answer.  The kernel compares the residual of its own solve with the size of the terms and must flag such designs; the
+    reference's pivoted LU (model.py:55) solves them, so whatever is NOT flagged must agree with it."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(6)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.auto_solver == "direct"
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="direct")
+    s = O.Structure(len(fixed), edges, fixed)
+    model = O.Model(s, loads, xyz[s.fixed_nodes])
+    first = int(plan.free[plan.solver_perm[0]])                      # the node whose diagonal is the first pivot
+    incident = [e for e, (u, v) in enumerate(edges) if u == first or v == first]
+    rng = np.random.default_rng(0)
+    designs = []
+    for eps in (0.0, 1e-14, 1e-11, 1e-7, 1e-3):
+        q = 1.0 + 0.2 * rng.random(len(edges))
+        q[incident[0]] = -(q[incident[1:]].sum()) + eps               # the first diagonal entry, sum of the incident q, is eps
+        designs.append(q)
+    out = ev.forward(np.stack(designs))
+    status = out["status"].cpu().numpy()
+    assert status[0] != 0                                              # an exact zero pivot is always flagged
+    for b, q in enumerate(designs):
+        if status[b] == 0:
+            ref = model(q)
+            assert _rel(out["xyz"].cpu().numpy()[b], ref.xyz) < 1e-7, (b, status)
+    assert status[-1] == 0                                             # a pivot of 1e-3 is harmless and must not be flagged
+
+
+@pytest.mark.parametrize("nfree,batch", [(5, 3), (12, 70), (20, 9), (27, 5), (30, 4)])
+def test_warp_and_cta_direct_kernels_agree_with_the_dense_oracle(nfree, batch):
+    """Bandwidths 5 ... 27 take the warp-per-design kernel (blocked LDL^T, DMMA trailing updates, register substitutions);
+    30 is beyond it and takes the CTA-per-design kernel.  Both against np.linalg.solve on the dense oracle."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(nfree)
+    plan = Plan(len(fixed), edges, fixed)
+    if plan.auto_solver != "direct":
+        pytest.skip("band does not fit shared memory")
+    ev = Evaluator(plan, loads, xyz[plan.fixed], solver="direct")
+    q = -W.sample_q(q0, batch, seed=13, spread=0.5, relative=True)     # compression: negative definite K
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.05)
+    out = ev.loss_and_grad(prog, q, outputs=STATE)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    for b in sorted({0, batch // 2, batch - 1}):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.05)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert _rel(out["forces"].cpu().numpy()[b], st.forces) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
