@@ -269,7 +269,7 @@ def gpu_arm(args, rank, world, local_rank):
     flush = working_set < 2 * L2_BYTES
     flush_buf = torch.empty(2 * L2_BYTES // 8, dtype=torch.float64, device=device) if flush else None
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None      # sampled from the warm-up on: short steps last < 200 ms
+    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get("DFDM_BENCH_SAMPLER", "1") != "0" else None      # sampled from the warm-up on: short steps last < 200 ms
     for _ in range(args.warmup):
         out, loss_x, dq_x = step()
     torch.cuda.synchronize()
@@ -298,13 +298,17 @@ def gpu_arm(args, rank, world, local_rank):
             ev_.record()
         step()                                          # untimed pre-roll: the device is busy (clocks up) when the first timed step starts
         step()
+        host_ms = []
         for k in range(args.steps):
             if flush:
                 flush_buf.fill_(float(k))
             starts[k].record()
+            h0 = time.perf_counter()
             step()
+            host_ms.append((time.perf_counter() - h0) * 1e3)
             ends[k].record()
         torch.cuda.synchronize()
+        last["ms_steps_host"] = host_ms
         if world > 1:
             dist.barrier()
         count = _lib.launch_count() - launches0
@@ -323,6 +327,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     ms_total, launches, _ = timed_region(False)
     ms_steps = [round(v, 3) for v in last["ms_steps"]]
+    ms_steps_host = [round(v, 3) for v in last["ms_steps_host"]]
     value = batch * world * args.steps / (ms_total * 1e-3)
     prof_ms, prof_count, ms_profiled = [0.0] * 8, [0] * 8, 0.0
     if solver == "pcg" and not args.no_profile:
@@ -330,26 +335,42 @@ def gpu_arm(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: host buffers through the C ABI, copies inside the timed region --------------------
-    loss_h = torch.empty(batch, dtype=torch.float64).pin_memory().numpy()
-    dq_h = torch.empty(batch, E, dtype=torch.float64).pin_memory().numpy()
-    status_h = torch.empty(batch, dtype=torch.int32).pin_memory().numpy()
+    # Every step copies its q in from pinned host memory and its losses, gradients and verdicts back out.  Measured twice:
+    # one call at a time (`serial`: copy in, kernels, copy out, strictly in sequence) and as a stream of batches issued by
+    # two host threads, whose calls take turns with the kernels so that one step's copies run under the other's kernels
+    # (Evaluator.loss_and_grad_host_many; each thread has output buffers of its own).
+    def pinned(*shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype).pin_memory().numpy()
+    n_threads = 2
+    outs = [(pinned(batch), pinned(batch, E), pinned(batch, dtype=torch.int32)) for _ in range(n_threads)]
+    loss_h, dq_h, status_h = outs[0]
     q_np = q_host.numpy()
-    ev.loss_and_grad_host(prog, q_np, loss_h, dq_h, status_h)     # warm the cached arena
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ev.loss_and_grad_host(prog, q_np, loss_h, dq_h, status_h)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te[0])
+
+    def e2e_region(threads):
+        batches = [(q_np,) + outs[k % threads] for k in range(args.steps)]
+        ev.loss_and_grad_host_many(prog, batches[:threads], threads=threads)     # warm the cached arenas
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ev.loss_and_grad_host_many(prog, batches, threads=threads)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te[0])
+
+    e2e_serial_s = e2e_region(1)
+    e2e_stream_s = e2e_region(n_threads) if args.steps >= n_threads else e2e_serial_s
+    e2e_s = min(e2e_serial_s, e2e_stream_s)
+    e2e_api = ("dfdm_loss_and_grad_host on pinned host buffers, one call per step, issued by %d host threads: the calls take turns with the "
+               "kernels and one step's copies run under the other's kernels" % n_threads) if e2e_stream_s < e2e_serial_s else \
+              "dfdm_loss_and_grad_host on pinned host buffers, one call at a time"
     h2d = q_np.nbytes + ev.loads_host.nbytes + ev.xyz_fixed_host.nbytes
     d2h = loss_h.nbytes + dq_h.nbytes + status_h.nbytes
-    same = bool(np.allclose(loss_h, out["loss"].cpu().numpy(), rtol=1e-12, atol=0))
+    ref_loss = out["loss"].cpu().numpy()
+    same = all(bool(np.allclose(o[0], ref_loss, rtol=1e-12, atol=0)) and bool(np.all(o[2] == status)) for o in outs)
 
     if rank != 0:
         return None
@@ -372,8 +393,9 @@ def gpu_arm(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": batch * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world,
-                    "api": "dfdm_loss_and_grad_host (pinned host buffers; the batch is cut into chunks whose copies run under the kernels of the neighbouring chunk)"},
-            "gpu_launches": launches, "ms_steps": ms_steps}
+                    "api": e2e_api, "serial": batch * world * args.steps / e2e_serial_s,
+                    "streamed_%d_threads" % n_threads: batch * world * args.steps / e2e_stream_s},
+            "gpu_launches": launches, "ms_steps": ms_steps, "ms_steps_host_enqueue": ms_steps_host}
     if solver == "pcg" and sum(prof_count) == 0:
         line["roofline"] = {"bound": "hbm", "kernel": "whole step (per-kernel table skipped: --no-profile)", "achieved": None, "peak": peak, "unit": "GB/s",
                             "frac": None, "traffic": None, "peak_source": peak_src}

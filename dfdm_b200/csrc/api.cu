@@ -198,10 +198,20 @@ static int dispatch(const dfdm_plan* plan, const dfdm_goalprog* prog, Eval& ev, 
     return solver == DFDM_SOLVER_DIRECT ? run_direct(ev) : run_pcg(ev);
 }
 
-// cached per-device arena of the *_host entry points (created on first use; the caller holds `busy` while it uses it)
-static Plan::Arena& arena_ref(const Plan& P, int device) {
+// cached per-device arenas of the *_host entry points (created on first use; the caller holds `busy` of the slot it uses)
+static Plan::ArenaSet& arena_ref(const Plan& P, int device) {
     std::lock_guard<std::mutex> lock(P.mu);
     return P.arena[device];
+}
+
+// Host calls from several threads share a device by taking turns with its SMs: the kernels of one call at a time (two
+// PCG solves interleaved would each run slower and double the working set), while the copies of the other calls - on
+// their own streams, into their own arenas - run underneath.
+static std::mutex& compute_turn(int device) {
+    static std::mutex mu;
+    static std::map<int, std::mutex> turns;
+    std::lock_guard<std::mutex> lock(mu);
+    return turns[device];
 }
 
 static int arena_prepare(Plan::Arena& a, int64_t bytes) {
@@ -286,13 +296,14 @@ void dfdm_plan_destroy(dfdm_plan* plan) {
         int prev = 0;
         cudaGetDevice(&prev);
         cudaSetDevice(kv.first);
-        Plan::Arena& a = kv.second;
-        if (a.ptr) cudaFree(a.ptr);
-        for (void* st : a.stream)
-            if (st) cudaStreamDestroy(static_cast<cudaStream_t>(st));
-        for (int k = 0; k < Plan::kHostChunksMax; ++k) {
-            if (a.ev_in[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_in[k]));
-            if (a.ev_done[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_done[k]));
+        for (Plan::Arena& a : kv.second.slot) {
+            if (a.ptr) cudaFree(a.ptr);
+            for (void* st : a.stream)
+                if (st) cudaStreamDestroy(static_cast<cudaStream_t>(st));
+            for (int k = 0; k < Plan::kHostChunksMax; ++k) {
+                if (a.ev_in[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_in[k]));
+                if (a.ev_done[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_done[k]));
+            }
         }
         cudaSetDevice(prev);
     }
@@ -480,8 +491,17 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     };
     Bump count(nullptr);
     layout(count);
-    Plan::Arena& A = arena_ref(*plan, device);
-    std::lock_guard<std::mutex> busy(A.busy);              // the arena and its streams belong to this call until it returns
+    // an arena and its streams belong to this call until it returns.  The first free slot: a caller on its own always
+    // gets slot 0 (one arena's worth of memory); concurrent callers spread over the slots and queue on slot 0 beyond.
+    Plan::ArenaSet& slots = arena_ref(*plan, device);
+    Plan::Arena* slot = nullptr;
+    std::unique_lock<std::mutex> busy;
+    for (int k = 0; k < Plan::kArenaSlots && !slot; ++k) {
+        std::unique_lock<std::mutex> attempt(slots.slot[k].busy, std::try_to_lock);
+        if (attempt.owns_lock()) { busy = std::move(attempt); slot = &slots.slot[k]; }
+    }
+    if (!slot) { busy = std::unique_lock<std::mutex>(slots.slot[0].busy); slot = &slots.slot[0]; }
+    Plan::Arena& A = *slot;
     rc = arena_prepare(A, count.off);
     if (rc) return rc;
     Bump real(static_cast<char*>(A.ptr));
@@ -497,6 +517,9 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
         DFDM_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(A.ev_in[c]), s_in));
     }
     auto at = [](double* p, int64_t off) { return p ? p + off : nullptr; };
+    // the kernels of this call, in its turn on the device; the copies above and the wait below stay outside the turn, so
+    // another thread's call copies in while this one computes and computes while this one copies out
+    std::unique_lock<std::mutex> turn(compute_turn(device));
     for (int c = 0; c < nchunks && rc == DFDM_OK; ++c) {
         const int64_t b0 = cb[c], nb = cb[c + 1] - cb[c];
         DFDM_CUDA_OK(cudaStreamWaitEvent(s_cmp, static_cast<cudaEvent_t>(A.ev_in[c]), 0));
@@ -522,6 +545,7 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
             break;
         if (status) DFDM_CUDA_OK(cudaMemcpyAsync(status + b0, d_status + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
     }
+    turn.unlock();
     // the arena is released (and may be reused by another thread) on return: nothing of this call may still be in flight
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
     if (rc) return rc;

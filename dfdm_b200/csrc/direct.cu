@@ -471,11 +471,14 @@ __host__ __device__ inline int direct_ld(int nf, bool warp) { return warp ? ((nf
 
 // One design, start to finish, by the `nt` threads of a group (a whole CTA, or one warp of it when WARP): tid = index in
 // the group, smem = the group's shared memory.
-template <bool WARP>
+// MODE 0: a CTA with the column-by-column factorisation; 1: one warp on its own; 2: a CTA (a "team") whose first warp
+// factors and substitutes with the warp routines while all its warps share the node / edge passes
+template <int MODE>
 __device__ void eval_design(const DirectArgs& a, const int b, double* smem, const int tid, const int nt, int* s_bad) {
+    constexpr bool WARP = MODE == 1, TEAM = MODE == 2;
     const PlanDev& P = a.P;
     const int nf = P.nf, n = P.n, E = P.E, w = P.w;
-    const int LD = direct_ld(nf, WARP);
+    const int LD = direct_ld(nf, WARP || TEAM);
     double* D = smem;
     double* rhs = D + (size_t)(w + 1) * LD;
     double* lcol = rhs + 3 * (size_t)nf;         // CTA kernel only
@@ -532,6 +535,9 @@ __device__ void eval_design(const DirectArgs& a, const int b, double* smem, cons
         // ---- banded LDL^T, right-looking, in place ---------------------------------------------------
         if (WARP) {
             bad_w = band_ldlt_warp(D, nf, w, LD);
+        } else if (TEAM) {
+            if (tid < 32 && band_ldlt_warp(D, nf, w, LD) && tid == 0) *s_bad = 1;
+            __syncthreads();
         } else if (w == 1 && a.chain_off >= 0) {
             chain_factor(D, nf, LD, smem + a.chain_off, s_bad);
         } else if (w == 1) {
@@ -582,6 +588,7 @@ __device__ void eval_design(const DirectArgs& a, const int b, double* smem, cons
 
         // ---- forward solve and equilibrium state ------------------------------------------------------
         if (WARP) band_solve_warp(D, rhs, nf, w, LD);
+        else if (TEAM) { if (tid < 32) band_solve_warp(D, rhs, nf, w, LD); __syncthreads(); }
         else if (w == 1 && a.chain_off >= 0) chain_solve(D, rhs, nf, LD, smem + a.chain_off);
         else band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
         for (int i = tid; i < n; i += nt) {
@@ -711,6 +718,7 @@ __device__ void eval_design(const DirectArgs& a, const int b, double* smem, cons
             }
             cta_sync(nt);
             if (WARP) band_solve_warp(D, rhs, nf, w, LD);                                           // K symmetric: same factor
+            else if (TEAM) { if (tid < 32) band_solve_warp(D, rhs, nf, w, LD); __syncthreads(); }
             else if (w == 1 && a.chain_off >= 0) chain_solve(D, rhs, nf, LD, smem + a.chain_off);
             else band_solve(D, rhs, nf, w, LD, nt, a.k_shift);
             for (int e = tid; e < E; e += nt) {
@@ -738,7 +746,15 @@ __device__ void eval_design(const DirectArgs& a, const int b, double* smem, cons
 __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
     extern __shared__ double smem[];
     __shared__ int s_bad;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<false>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<0>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+}
+
+// one CTA per design with the warp routines for the factor and the substitutions: small batches, where a warp per design
+// would leave most of every SM idle during the node / edge passes
+__global__ void __launch_bounds__(256) k_direct_team(DirectArgs a) {
+    extern __shared__ double smem[];
+    __shared__ int s_bad;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<2>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
 }
 
 // the same body for long chains: 1 024 threads (64 registers) - the partition solver is light, the node / edge passes over
@@ -746,7 +762,7 @@ __global__ void __launch_bounds__(256) k_direct_eval(DirectArgs a) {
 __global__ void __launch_bounds__(1024) k_direct_chain(DirectArgs a) {
     extern __shared__ double smem[];
     __shared__ int s_bad;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<false>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<0>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
 }
 
 // one warp per design; `stride` doubles of shared memory per warp
@@ -754,7 +770,7 @@ __global__ void __launch_bounds__(256) k_direct_warp(DirectArgs a, int stride) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     double* mine = smem + (size_t)warp * stride;
-    for (int b = blockIdx.x * warps + warp; b < a.B; b += gridDim.x * warps) eval_design<true>(a, b, mine, threadIdx.x & 31, 32, nullptr);
+    for (int b = blockIdx.x * warps + warp; b < a.B; b += gridDim.x * warps) eval_design<1>(a, b, mine, threadIdx.x & 31, 32, nullptr);
 }
 
 int64_t direct_workspace(const Plan& P, int B, bool adjoint, bool has_prog) {
@@ -824,6 +840,32 @@ int run_direct(Eval& ev) {
     const int64_t per_design = factor_part + state_part;
     if (!warp_off && w >= 2 && w <= kWarpMaxW && per_design * 8 <= 100 * 1024) {
         a.state_off = (int)factor_part;
+        // A warp per design fills the SMs only when there are many designs per SM.  Below `team_below` designs per SM a
+        // CTA per design ("team": warp 0 factors and substitutes, every warp shares the passes over nodes and edges)
+        // is the faster shape (dome, 512 designs = 3.5 per SM: 63.6 against 85.8 us; pillow / pringle at 6.9 per SM: a warp per
+        // design wins by 1-6 %); DFDM_DIRECT_TEAM_BELOW / DFDM_DIRECT_TEAM_THREADS are there for the sweep that set them
+        // (profiles/r02_direct_team_sweep.json).
+        static const int team_below = std::getenv("DFDM_DIRECT_TEAM_BELOW") ? std::atoi(std::getenv("DFDM_DIRECT_TEAM_BELOW")) : 5;
+        static const int team_threads = std::getenv("DFDM_DIRECT_TEAM_THREADS") ? std::atoi(std::getenv("DFDM_DIRECT_TEAM_THREADS")) : 128;
+        if (B < (int64_t)team_below * sms) {
+            const size_t smem = (size_t)per_design * 8;
+            if (smem > 48 * 1024) {
+                static std::mutex mu;
+                static std::map<int, size_t> configured;
+                std::lock_guard<std::mutex> lock(mu);
+                if (configured[dev] < smem) {
+                    DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_team, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    configured[dev] = smem;
+                }
+            }
+            const int nt = std::max(32, std::min(256, team_threads & ~31));
+            DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_team, nt, smem));
+            if (per_sm < 1) per_sm = 1;
+            const int grid = (int)std::min<int64_t>(B, (int64_t)sms * per_sm);
+            k_direct_team<<<grid, nt, smem, ev.stream>>>(a);
+            DFDM_LAUNCH_OK("k_direct_team");
+            return DFDM_OK;
+        }
         // designs per CTA: up to 8 warps, as many as fit ~100 KB so that two CTAs share an SM; fewer when the batch is small
         int warps = (int)std::max<int64_t>(1, std::min<int64_t>(8, (100 * 1024) / (per_design * 8)));
         while (warps > 1 && (B + warps - 1) / warps < sms) warps >>= 1;      // spread a small batch over the SMs first

@@ -128,9 +128,11 @@ struct Plan {
     mutable std::map<int, PlanDev> dev;
     mutable std::map<int, PlanDev> dev_pcg;
     mutable std::map<int, void*> dev_block;
-    // One per device, for the *_host entry points: device memory, three private streams (copy in, compute, copy out) and
-    // the events that chain them.  `busy` is held for a whole host call: *_host calls on one (plan, device) are serialised.
+    // For the *_host entry points, kArenaSlots per device: device memory, three private streams (copy in, compute, copy out)
+    // and the events that chain them.  `busy` is held for a whole host call; a second thread calling while the first slot
+    // is busy takes the second, so that its copies run under the first call's kernels (api.cu: host_eval).
     static constexpr int kHostChunksMax = 8;
+    static constexpr int kArenaSlots = 2;
     struct Arena {
         void* ptr = nullptr;
         int64_t bytes = 0;
@@ -139,7 +141,8 @@ struct Plan {
         void* ev_in[kHostChunksMax] = {nullptr};
         void* ev_done[kHostChunksMax] = {nullptr};
     };
-    mutable std::map<int, Arena> arena;
+    struct ArenaSet { Arena slot[kArenaSlots]; };
+    mutable std::map<int, ArenaSet> arena;
 };
 
 // One goal, flattened.  mode 0: contributes scale * weight * (p - t)^2 per component;

@@ -253,6 +253,36 @@ class Evaluator:
                                                        C.c_void_p(0) if dq is None else _np_ptr(dq), _np_ptr(status),
                                                        C.byref(self.options)))
 
+    def loss_and_grad_host_many(self, prog, batches, threads=2):
+        """A stream of batches with host buffers: `batches` is a list of (q, loss, dq, status) NumPy buffers (pinned for the
+        overlap), one dfdm_loss_and_grad_host call each.  Batch i is evaluated by host thread i % threads, every thread
+        working through its batches in order, so batches i and i + threads may reuse the same buffers and no others may.
+        The library gives every call in flight an arena and streams of its own and lets the calls take turns with the
+        kernels (include/dfdm_b200.h, host-buffer variants): one call's copies run under another call's kernels.
+        Returns when every batch is back on the host."""
+        import threading
+        threads = max(1, min(int(threads), len(batches)))
+        if threads == 1:
+            for b in batches:
+                self.loss_and_grad_host(prog, *b)
+            return
+        errors = []
+
+        def work(t):
+            try:
+                for b in batches[t::threads]:
+                    self.loss_and_grad_host(prog, *b)
+            except BaseException as exc:                                 # handed to the caller below
+                errors.append(exc)
+
+        pool = [threading.Thread(target=work, args=(t,), name="dfdm-host-%d" % t) for t in range(threads)]
+        for th in pool:
+            th.start()
+        for th in pool:
+            th.join()
+        if errors:
+            raise errors[0]
+
     def forward_host(self, q, xyz=None, residuals=None, vectors=None, lengths=None, forces=None, status=None):
         B = q.shape[0]
         args = [C.c_void_p(0) if a is None else _np_ptr(a) for a in (xyz, residuals, vectors, lengths, forces, status)]

@@ -236,6 +236,11 @@ DFDM_API int dfdm_vjp(const dfdm_plan* plan, int32_t batch,
  * the batch whole (measured: its latency-bound multigrid levels make two half batches 26 % slower than one whole,
  * more than the hidden copies return; DFDM_HOST_CHUNKS=k forces k chunks for experiments).  Pinned host buffers are
  * needed for any overlap (pageable ones still work, serialised by the driver).
+ * Threads: the calls may be made from several host threads on one plan and device.  Each call in flight owns one of two
+ * cached arenas (memory, streams) per (plan, device); the calls take turns with the kernels and copy outside their turn,
+ * so with two threads, each evaluating batches of its own, the copies of one call run under the kernels of the other -
+ * the way to keep a GPU busy with a stream of batches whose buffers live on the host (bench.py's `e2e`).  A third
+ * concurrent call waits for the first arena.
  */
 DFDM_API int dfdm_forward_host(const dfdm_plan* plan, int32_t batch, const double* q, const double* loads, const double* xyz_fixed,
                       double* xyz, double* residuals, double* vectors, double* lengths, double* forces,

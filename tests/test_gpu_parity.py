@@ -445,9 +445,11 @@ def test_grid256_matches_sparse_oracle():
     assert np.max(np.abs(res[:, plan.free])) < 1e-9 * np.abs(res).max()
 
 
-def test_host_calls_pipeline_in_chunks_and_serialise_per_plan():
-    """dfdm_loss_and_grad_host cuts a large batch into chunks whose copies overlap the kernels; two threads sharing one plan
-    (different batch sizes, so the cached arena is regrown under them) must each get the device path's answers."""
+def test_host_calls_from_several_threads_share_a_plan():
+    """dfdm_loss_and_grad_host from several threads on one plan: every call in flight owns one of two cached arenas, the
+    calls take turns with the kernels, a third concurrent call queues for an arena.  Different batch sizes, so the arenas
+    are regrown under the threads; each must get the device path's answers.  Then the same through the helper that
+    issues a stream of batches from two threads (Evaluator.loss_and_grad_host_many)."""
     import threading
     from dfdm_b200 import workloads as W
     edges, fixed, xyz, loads, q0 = W.grid_arrays(24)
@@ -474,12 +476,20 @@ def test_host_calls_pipeline_in_chunks_and_serialise_per_plan():
         except Exception as exc:                       # noqa: BLE001 (reported to the main thread)
             errors.append(exc)
 
-    threads = [threading.Thread(target=worker, args=(200, 3)), threading.Thread(target=worker, args=(37, 6))]
+    threads = [threading.Thread(target=worker, args=(200, 3)), threading.Thread(target=worker, args=(37, 6)),
+               threading.Thread(target=worker, args=(64, 4))]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     assert not errors, errors
+    outs = [(np.empty(200), np.empty((200, len(edges))), np.empty(200, dtype=np.int32)) for _ in range(2)]
+    qc = np.ascontiguousarray(q)
+    ev.loss_and_grad_host_many(prog, [(qc,) + outs[k % 2] for k in range(5)], threads=2)
+    for loss, dq, status in outs:
+        assert np.all(status == 0)
+        assert np.allclose(loss, loss_ref, rtol=1e-9, atol=0)
+        assert _rel(dq, dq_ref) < TOL_G
 
 
 @pytest.mark.parametrize("nfree,batch", [(40, 6), (64, 2), (96, 34)])
