@@ -250,7 +250,7 @@ def gpu_arm(args, rank, world, local_rank):
     #              slice pushed under the kernels of the next piece (--chunks), NCCL when the ranks cannot map each other
     #              (DFDM_PEER_GATHER=0 forces NCCL)
     #   root       rank 0 only receives them (a host-side optimiser on one rank)
-    #   losses     gradients stay with their designs, all losses everywhere (a sharded optimiser: B doubles on the wire)
+    #   losses     gradients stay with their designs, all losses everywhere (a sharded optimiser: B doubles on the wire) - default
     #   mean       ensemble mean of loss and gradient: one all-reduce of E + 1 doubles
     def evaluate(q_local):
         out = ev.loss_and_grad(prog, q_local)
@@ -589,8 +589,11 @@ def main():
     ap.add_argument("--pcg-rtol", type=float, default=0.0)
     ap.add_argument("--pcg-rtol-adjoint", type=float, default=0.0)
     ap.add_argument("--pcg-check-every", type=int, default=0)
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "root", "losses", "mean"],
-                    help="N > 1: what travels between the ranks after an evaluation (see gpu_arm)")
+    ap.add_argument("--exchange", default="losses", choices=["allgather", "root", "losses", "mean"],
+                    help="N > 1: what travels between the ranks after an evaluation (see gpu_arm).  Default: what the repo's own "
+                    "consumer of a sharded batch - the device-resident lock-step optimisers - needs: gradients stay with their "
+                    "designs, every rank learns every loss.  SURVEY.md 8(e)'s all-gather / gather-to-root of losses AND gradients: "
+                    "--exchange allgather / root")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1, allgather by peer stores: pieces of the local slice, each pushed under the next one's kernels "
                     "(measured: evaluating the slice in two pieces costs more than the overlap returns on the PCG path - 70.2 against 60.1 ms per step at N = 2)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch designs per GPU; strong: --batch designs in all")

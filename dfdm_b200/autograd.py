@@ -33,7 +33,7 @@ def _function():
 
         @staticmethod
         def forward(ctx, q, evaluator):
-            out = evaluator.forward(q.detach())
+            out = evaluator.forward(q.detach(), rescue=True)
             Evaluator.raise_on_status(out["status"])
             ctx.evaluator = evaluator
             ctx.save_for_backward(q.detach())
@@ -43,7 +43,7 @@ def _function():
         def backward(ctx, g_xyz, g_res, g_vec, g_len, g_for):
             q, = ctx.saved_tensors
             cots = [None if g is None else g.contiguous() for g in (g_xyz, g_res, g_vec, g_len, g_for)]
-            dq, status = ctx.evaluator.vjp(q, *cots)
+            dq, status = ctx.evaluator.vjp(q, *cots, rescue=True)
             Evaluator.raise_on_status(status)
             return dq, None
 

@@ -51,7 +51,7 @@ class Constraint:
         eqstate = _cached_state(q, model)
         cots = self.cotangents(eqstate, model)
         m = next(iter(cots.values())).shape[0]
-        dq, status = model.evaluator.vjp(np.repeat(q[None, :], m, axis=0), **cots)
+        dq, status = model.evaluator.vjp(np.repeat(q[None, :], m, axis=0), rescue=True, **cots)
         Evaluator.raise_on_status(status)
         return dq.cpu().numpy()
 

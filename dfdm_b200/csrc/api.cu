@@ -152,14 +152,13 @@ static int upload_prog(const GoalProg& G, int device, GoalProgDev& out) {
 }
 
 static int resolve_solver(const Plan& P, const dfdm_options* opt, int& solver) {
+    // AUTO: the fused shared-memory kernel when the banded factor fits a CTA's shared memory, PCG beyond.  DIRECT asked for
+    // by name beyond that limit takes the global-memory variant of the same factorisation (direct.cu: k_direct_global) - an
+    // order of magnitude slower per design than PCG on a definite K, but the one path that solves an indefinite K
+    // (mixed-sign q) at any size, as the reference's LU does (model.py:55).
     bool fits = direct_smem_bytes(P.nf, P.w) <= kDirectSmemLimit;
     solver = opt ? opt->solver : DFDM_SOLVER_AUTO;
     if (solver == DFDM_SOLVER_AUTO) solver = fits ? DFDM_SOLVER_DIRECT : DFDM_SOLVER_PCG;
-    if (solver == DFDM_SOLVER_DIRECT && !fits) {
-        set_error("direct solver requested but the banded factor (" + std::to_string(direct_smem_bytes(P.nf, P.w)) +
-                  " bytes) does not fit one CTA's shared memory; use DFDM_SOLVER_PCG");
-        return DFDM_EUNSUPPORTED;
-    }
     if (solver != DFDM_SOLVER_DIRECT && solver != DFDM_SOLVER_PCG) {
         set_error("unknown solver id");
         return DFDM_EINVAL;

@@ -48,6 +48,8 @@ struct DirectArgs {
     int state_off;                   // >= 0: the per-design state lives in shared memory, at this offset (doubles) of the group's block:
                                      // q[E], X[3n] (later Xbar), U[3E], L[E], F[E], Rbar[3n], Ubar[3E] - every pass then runs on shared
                                      // memory and only q comes in and loss / dq (and requested outputs) go out
+    double* band;                    // non-NULL: the band and the right-hand sides of CTA k live in GLOBAL memory at band + k * band_stride
+    int64_t band_stride;             // (doubles) - factors too large for shared memory (k_direct_global)
     const double *c_xyz, *c_res, *c_vec, *c_len, *c_for;
     double* loss;
     double* dq;
@@ -479,11 +481,11 @@ __device__ void eval_design(const DirectArgs& a, const int b, double* smem, cons
     const PlanDev& P = a.P;
     const int nf = P.nf, n = P.n, E = P.E, w = P.w;
     const int LD = direct_ld(nf, WARP || TEAM);
-    double* D = smem;
+    double* D = (MODE == 0 && a.band) ? a.band + (size_t)blockIdx.x * a.band_stride : smem;
     double* rhs = D + (size_t)(w + 1) * LD;
-    double* lcol = rhs + 3 * (size_t)nf;         // CTA kernel only
+    double* lcol = (MODE == 0 && a.band) ? smem : rhs + 3 * (size_t)nf;         // CTA kernel only
     double* lsc = lcol + (w + 1);
-    double* red = lsc + (w + 1);                 // 16 doubles
+    double* red = lsc + (w + 1);                 // 32 doubles: one per warp of the largest CTA
     int bad_w = 0;                               // warp kernel: the verdict lives in registers
     {
         const bool in_smem = a.state_off >= 0;
@@ -765,6 +767,16 @@ __global__ void __launch_bounds__(1024) k_direct_chain(DirectArgs a) {
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<0>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
 }
 
+// factors too large for shared memory: the band and the right-hand sides of a CTA's design live in global memory (its own
+// slot of the workspace - L2 resident while it is worked on), only the column scratch is in shared memory.  Same body, same
+// column-by-column sweep with two block barriers per column: ~2 us per column instead of ~0.2.  This is the path of last
+// resort - mixed-sign q (indefinite K, which CG cannot solve) on networks beyond the shared-memory limit.
+__global__ void __launch_bounds__(1024) k_direct_global(DirectArgs a) {
+    extern __shared__ double smem[];
+    __shared__ int s_bad;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) eval_design<0>(a, b, smem, threadIdx.x, blockDim.x, &s_bad);
+}
+
 // one warp per design; `stride` doubles of shared memory per warp
 __global__ void __launch_bounds__(256) k_direct_warp(DirectArgs a, int stride) {
     extern __shared__ double smem[];
@@ -773,10 +785,17 @@ __global__ void __launch_bounds__(256) k_direct_warp(DirectArgs a, int stride) {
     for (int b = blockIdx.x * warps + warp; b < a.B; b += gridDim.x * warps) eval_design<1>(a, b, mine, threadIdx.x & 31, 32, nullptr);
 }
 
+// global-memory variant: CTAs (= band slots in the workspace) and doubles per slot
+constexpr int kGlobalSlots = 296;
+static int64_t global_band_stride(int nf, int w) {
+    return (((int64_t)(w + 1) * direct_ld(nf, false) + 3 * (int64_t)nf) + 31) & ~(int64_t)31;
+}
+
 int64_t direct_workspace(const Plan& P, int B, bool adjoint, bool has_prog) {
     (void)has_prog;
     Bump bump(nullptr);
     int64_t n = P.n, E = P.E;
+    if (direct_smem_bytes(P.nf, P.w) > kDirectSmemLimit) bump.take<double>(std::min<int64_t>(B, kGlobalSlots) * global_band_stride(P.nf, P.w));
     bump.take<double>(B * n * 3);   // X
     bump.take<double>(B * n * 3);   // R
     bump.take<double>(B * E * 3);   // U
@@ -803,6 +822,11 @@ int run_direct(Eval& ev) {
     a.q = ev.q;
     a.loads = ev.loads;
     a.xfix = ev.xfix;
+    const bool global_band = direct_smem_bytes(P.nf, P.w) > kDirectSmemLimit;
+    if (global_band) {
+        a.band_stride = global_band_stride(P.nf, P.w);
+        a.band = bump.take<double>(std::min<int64_t>(B, kGlobalSlots) * a.band_stride);
+    }
     a.X = bump.take<double>(B * n * 3);
     a.R = bump.take<double>(B * n * 3);
     a.U = bump.take<double>(B * E * 3);
@@ -833,6 +857,41 @@ int run_direct(Eval& ev) {
     int dev = 0, sms = 0, per_sm = 0;
     DFDM_CUDA_OK(cudaGetDevice(&dev));
     DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (global_band) {
+        const int nt = 1024;
+        int tx = 4;
+        while (tx < 32 && tx < w) tx <<= 1;
+        int shift = 0;
+        while ((1 << shift) < tx) ++shift;
+        a.tx_shift = shift;
+        int kshift = 0;
+        while ((1 << kshift) < w) ++kshift;
+        a.k_shift = kshift;
+        int64_t smem = 8 * (2 * (int64_t)(w + 1) + 32);
+        if (w == 1 && P.nf >= 6) {
+            a.chain_off = (int)(smem / 8);
+            smem += 8 * (int64_t)kChainScratch;
+        }
+        if (smem > 200 * 1024) {
+            set_error("direct solver: half-bandwidth " + std::to_string(w) + " is beyond the global-memory variant's column scratch");
+            return DFDM_EUNSUPPORTED;
+        }
+        if (smem > 48 * 1024) {
+            static std::mutex mu;
+            static std::map<int, int64_t> configured;
+            std::lock_guard<std::mutex> lock(mu);
+            if (configured[dev] < smem) {
+                DFDM_CUDA_OK(cudaFuncSetAttribute(k_direct_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = smem;
+            }
+        }
+        DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_global, nt, (size_t)smem));
+        if (per_sm < 1) per_sm = 1;
+        const int grid = (int)std::min<int64_t>(std::min<int64_t>(B, kGlobalSlots), (int64_t)sms * per_sm);
+        k_direct_global<<<grid, nt, (size_t)smem, ev.stream>>>(a);
+        DFDM_LAUNCH_OK("k_direct_global");
+        return DFDM_OK;
+    }
     // ---- one warp per design: narrow bands whose factor leaves room for several designs per SM ------------------------
     static const bool warp_off = std::getenv("DFDM_DIRECT_WARP") && std::atoi(std::getenv("DFDM_DIRECT_WARP")) == 0;
     const int64_t factor_part = (int64_t)(w + 1) * direct_ld(P.nf, true) + 3 * (int64_t)P.nf + 2 * (int64_t)(w + 1) + 16;   // doubles

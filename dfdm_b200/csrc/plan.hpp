@@ -183,7 +183,7 @@ int build_plan(int32_t n, int32_t E, const int32_t* edges, const uint8_t* is_fix
 // shared-memory footprint of the fused direct kernel for half-bandwidth w
 inline int64_t direct_smem_bytes(int nf, int w) {
     int64_t ld = (int64_t)nf | 1;                      // odd leading dimension: conflict-free diagonals
-    return 8 * ((int64_t)(w + 1) * ld + 3 * (int64_t)nf + 2 * (int64_t)(w + 1) + 16);
+    return 8 * ((int64_t)(w + 1) * ld + 3 * (int64_t)nf + 2 * (int64_t)(w + 1) + 32);
 }
 constexpr int64_t kDirectSmemLimit = 200 * 1024;
 

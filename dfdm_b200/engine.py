@@ -150,6 +150,27 @@ class Evaluator:
         self.xyz_fixed = torch.from_numpy(xyz_fixed).to(self.device) if plan.n_fixed else torch.zeros(1, 3, dtype=torch.float64, device=self.device)
         self._ws = None
         self._ws_batch = 0
+        self._solver_name = solver
+        self._twin = None
+
+    # -- designs the PCG path cannot solve -----------------------------------------------------------------
+    # CG needs a definite K: force densities of one sign.  The reference's LU (model.py:55) also solves the indefinite K of
+    # a mixed-sign q, which the optimisers do wander into when q is unbounded (pillow.py:70, dome_constraints.py:80).  With
+    # rescue=True the entry points below look at the verdicts (one device-to-host read) and hand the designs the PCG path
+    # gave up on to the direct solver's global-memory variant (DFDM_SOLVER_DIRECT beyond the shared-memory limit) - slow,
+    # exact, and flagged itself should a tiny pivot spoil it.  The API layer (EquilibriumModel, Loss, constraints) asks
+    # for it; batched device loops (bench.py, the lock-step optimisers) do not and keep their hands off the host.
+
+    def _failed_rows(self, status):
+        if self._solver_name != "auto" or self.plan.auto_solver != "pcg":
+            return None
+        bad = self.torch.nonzero((status == _lib.STATUS_NOT_CONVERGED) | (status == _lib.STATUS_NONFINITE)).flatten()
+        return bad if bad.numel() else None
+
+    def _direct_twin(self):
+        if self._twin is None:
+            self._twin = Evaluator(self.plan, self.loads_host, self.xyz_fixed_host, device=self.device, solver="direct")
+        return self._twin
 
     # -- plumbing ------------------------------------------------------------------------------------
 
@@ -184,7 +205,7 @@ class Evaluator:
 
     # -- device entry points ---------------------------------------------------------------------------
 
-    def forward(self, q, outputs=STATE):
+    def forward(self, q, outputs=STATE, rescue=False):
         """EquilibriumModel.__call__ for a batch: dict of device tensors + ``status`` int32[B]."""
         torch = self.torch
         q = self._q(q)
@@ -199,9 +220,14 @@ class Evaluator:
                                             C.byref(self.options), self._stream()))
         out["status"] = status
         out["q"] = q
+        bad = self._failed_rows(status) if rescue else None
+        if bad is not None:
+            sub = self._direct_twin().forward(q[bad], outputs=outputs)
+            for k in tuple(outputs) + ("status",):
+                out[k][bad] = sub[k]
         return out
 
-    def loss_and_grad(self, prog, q, grad=True, outputs=()):
+    def loss_and_grad(self, prog, q, grad=True, outputs=(), rescue=False):
         """Loss.__call__ + grad(loss): ``loss[B]``, ``dq[B,E]`` (None if grad=False), ``status[B]``, optional state."""
         torch = self.torch
         q = self._q(q)
@@ -217,9 +243,14 @@ class Evaluator:
                                                   _ptr(loss), _ptr(dq), *[_ptr(out.get(k)) for k in self.STATE], _ptr(status),
                                                   _ptr(ws), ws.numel(), C.byref(self.options), self._stream()))
         out.update({"loss": loss, "dq": dq, "status": status, "q": q})
+        bad = self._failed_rows(status) if rescue else None
+        if bad is not None:
+            sub = self._direct_twin().loss_and_grad(prog, q[bad], grad=grad, outputs=outputs)
+            for k in tuple(outputs) + ("loss", "status") + (("dq",) if grad else ()):
+                out[k][bad] = sub[k]
         return out
 
-    def vjp(self, q, xyz=None, residuals=None, vectors=None, lengths=None, forces=None):
+    def vjp(self, q, xyz=None, residuals=None, vectors=None, lengths=None, forces=None, rescue=False):
         """q-bar [B,E] for cotangents of the state arrays (any subset)."""
         torch = self.torch
         q = self._q(q)
@@ -240,6 +271,11 @@ class Evaluator:
             _lib.check(_lib.lib.dfdm_vjp(self.plan.handle, B, _ptr(q), _ptr(self.loads), _ptr(self.xyz_fixed),
                                         *[_ptr(c) for c in cots], _ptr(dq), _ptr(status), _ptr(ws), ws.numel(),
                                         C.byref(self.options), self._stream()))
+        bad = self._failed_rows(status) if rescue else None
+        if bad is not None:
+            sub_dq, sub_status = self._direct_twin().vjp(q[bad], *[None if c is None else c[bad] for c in cots])
+            dq[bad] = sub_dq
+            status[bad] = sub_status
         return dq, status
 
     # -- host entry points (copies inside the call) ------------------------------------------------------

@@ -38,7 +38,7 @@ class EquilibriumModel:
     def __call__(self, q):
         q = np.asarray(q, dtype=np.float64)
         single = q.ndim == 1
-        out = self.evaluator.forward(q)
+        out = self.evaluator.forward(q, rescue=True)
         Evaluator.raise_on_status(out["status"])
         arrays = {k: out[k].cpu().numpy() for k in Evaluator.STATE}
         if single:

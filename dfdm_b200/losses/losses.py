@@ -158,7 +158,7 @@ class Loss:
         key = (id(model), q.shape, q.tobytes()) if q.nbytes <= _CACHE_BYTES else None
         if key is not None and self._last is not None and self._last[0] == key and (self._last[2] is not None or not grad):
             return self._last[1], self._last[2]
-        out = model.evaluator.loss_and_grad(self.program(model), q, grad=grad)
+        out = model.evaluator.loss_and_grad(self.program(model), q, grad=grad, rescue=True)
         Evaluator.raise_on_status(out["status"])
         loss = out["loss"].cpu().numpy()
         dq = out["dq"].cpu().numpy() if grad else None

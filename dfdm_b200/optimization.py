@@ -141,7 +141,7 @@ class StackedConstraints:
                     stacked[name] = np.zeros(shapes[name])
                 stacked[name][row:row + m] = arr
             row += m
-        dq, status = model.evaluator.vjp(np.repeat(q[None, :], total, axis=0), **stacked)
+        dq, status = model.evaluator.vjp(np.repeat(q[None, :], total, axis=0), rescue=True, **stacked)
         Evaluator.raise_on_status(status)
         return dq.cpu().numpy()
 

@@ -54,7 +54,9 @@ extern "C" {
 
 /* solver selection */
 #define DFDM_SOLVER_AUTO 0
-#define DFDM_SOLVER_DIRECT 1   /* banded LDL^T in shared memory, one CTA per design, whole eval fused */
+#define DFDM_SOLVER_DIRECT 1   /* banded LDL^T, whole evaluation fused in one kernel: in shared memory (a warp or a CTA per design) when the
+                                  factor fits; asked for by name beyond that, the same factorisation with the band in global memory
+                                  (slow; the path that solves the indefinite K of a mixed-sign q at any size) */
 #define DFDM_SOLVER_PCG 2      /* CG on batch-interleaved CSR, preconditioned by aggregation multigrid (or Jacobi: DFDM_PRECOND_*) */
 
 typedef struct dfdm_plan dfdm_plan;

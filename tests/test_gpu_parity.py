@@ -570,3 +570,54 @@ def test_warp_and_cta_direct_kernels_agree_with_the_dense_oracle(nfree, batch):
         assert _rel(out["forces"].cpu().numpy()[b], st.forces) < TOL_X
         assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
         assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+
+
+def test_direct_solver_beyond_shared_memory_and_the_rescue_of_mixed_sign_designs():
+    """48 x 48 free nodes: the banded factor (about 0.9 MB) is past the shared-memory limit, so DFDM_SOLVER_AUTO means PCG.
+    (1) DFDM_SOLVER_DIRECT by name takes the global-memory variant of the factorisation: against SuperLU on a definite K.
+    (2) mixed-sign q makes K indefinite, CG gives up, and with rescue=True the evaluator hands exactly those designs to
+    that variant: against SuperLU again (the reference's LU, model.py:55, solves such designs at any size)."""
+    from dfdm_b200 import workloads as W
+    edges, fixed, xyz, loads, q0 = W.grid_arrays(48)
+    plan = Plan(len(fixed), edges, fixed)
+    assert plan.auto_solver == "pcg"
+    lengths0 = np.linalg.norm(xyz[edges[:, 1]] - xyz[edges[:, 0]], axis=1)
+    goals = [("EdgeLength", e, 0, 1.0, [lengths0[e]]) for e in range(len(edges))]
+    prog = GoalProgram(plan, goals, [("SquaredError", 1.0)], 0.1)
+    sm = O.SparseModel(len(fixed), edges, fixed, loads, xyz[plan.fixed])
+    q = W.sample_q(q0, 4, seed=21, spread=0.4, relative=True)
+
+    direct = Evaluator(plan, loads, xyz[plan.fixed], solver="direct")
+    out = direct.loss_and_grad(prog, q, outputs=STATE)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    for b in (0, 3):
+        loss, dq, st = sm.loss_and_grad_edge_length(q[b], lengths0, 1.0, 0.1)
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < TOL_X
+        assert _rel(out["forces"].cpu().numpy()[b], st.forces) < TOL_X
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-9 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < TOL_G
+
+    rng = np.random.default_rng(3)
+    q_mixed = q.copy()
+    for b in (1, 2):                                                   # designs 0 and 3 stay definite
+        flip = rng.random(len(edges)) < 0.3
+        q_mixed[b, flip] *= -1.0
+    auto = Evaluator(plan, loads, xyz[plan.fixed])
+    plain = auto.loss_and_grad(prog, q_mixed)
+    st_plain = plain["status"].cpu().numpy()
+    assert st_plain[0] == 0 and st_plain[3] == 0 and st_plain[1] != 0 and st_plain[2] != 0
+    out = auto.loss_and_grad(prog, q_mixed, outputs=STATE, rescue=True)
+    status = out["status"].cpu().numpy()
+    for b in range(4):
+        loss, dq, st = sm.loss_and_grad_edge_length(q_mixed[b], lengths0, 1.0, 0.1)
+        if status[b] != 0:                                             # the unpivoted factor may flag a design, never mislead
+            continue
+        assert _rel(out["xyz"].cpu().numpy()[b], st.xyz) < 1e-7
+        assert abs(float(out["loss"].cpu()[b]) - loss) < 1e-7 * abs(loss)
+        assert _rel(out["dq"].cpu().numpy()[b], dq) < 1e-5
+    assert status[0] == 0 and status[3] == 0 and (status[1] == 0 or status[2] == 0)
+    fwd = auto.forward(q_mixed, outputs=("xyz",), rescue=True)
+    ok = fwd["status"].cpu().numpy() == 0
+    assert ok[0] and ok[3] and (ok[1] or ok[2])
+    for b in np.nonzero(ok)[0]:
+        assert _rel(fwd["xyz"].cpu().numpy()[b], sm(q_mixed[b]).xyz) < 1e-7
