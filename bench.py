@@ -281,6 +281,7 @@ def gpu_arm(args, rank, world, local_rank):
     if world > 1:
         gather_ok = exchange_check(args.exchange, world, rank, batch, sharded.last_local, loss_x, dq_x, device)
     iters = _lib.last_pcg_iterations() if solver == "pcg" else (0, 0)
+    direct_kernel = _lib.last_direct_kernel() if solver == "direct" else None
 
     # ---- timed regions: device-resident inputs -------------------------------------------------------
     # (1) K steps with nothing but the step's own launches on the stream: `value`.
@@ -456,8 +457,8 @@ def gpu_arm(args, rank, world, local_rank):
         # direct path: one fused kernel per step; mandatory I/O only (q in, loss + dq out)
         alg = batch * (16.0 * E + 8.0)
         ms = ms_total / args.steps
-        line["roofline"] = {"bound": "hbm", "kernel": "k_direct_eval", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic_for("k_direct_eval", wl["name"]),
+        line["roofline"] = {"bound": "hbm", "kernel": direct_kernel, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic_for(direct_kernel, wl["name"]),
                             "peak_source": peak_src,
                             "note": "shared-memory factorisation: latency / FP64-issue bound, not HBM bound; fraction reported for completeness"}
         # FP64 view of the same kernel: banded LDL^T nf*w*(w+2) flops, two solves x 3 right-hand sides x (4 nf w + nf)

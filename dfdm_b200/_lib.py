@@ -37,7 +37,7 @@ TERM_KINDS = {"SquaredError": 0, "MeanSquaredError": 1, "PredictionError": 2}
 SYMBOLS = ["dfdm_last_error", "dfdm_abi_version", "dfdm_plan_create", "dfdm_plan_destroy", "dfdm_plan_get_info",
            "dfdm_plan_array", "dfdm_goalprog_create", "dfdm_goalprog_destroy", "dfdm_workspace_bytes", "dfdm_forward",
            "dfdm_loss_and_grad", "dfdm_vjp", "dfdm_forward_host", "dfdm_loss_and_grad_host", "dfdm_launch_count",
-           "dfdm_last_pcg_iterations", "dfdm_profile_enable", "dfdm_profile_read", "dfdm_peer_alloc", "dfdm_peer_open",
+           "dfdm_last_pcg_iterations", "dfdm_last_direct_kernel", "dfdm_profile_enable", "dfdm_profile_read", "dfdm_peer_alloc", "dfdm_peer_open",
            "dfdm_peer_close", "dfdm_peer_free", "dfdm_peer_push"]
 
 
@@ -85,6 +85,8 @@ def _load():
     lib.dfdm_launch_count.restype = i64
     lib.dfdm_last_pcg_iterations.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     lib.dfdm_last_pcg_iterations.restype = None
+    lib.dfdm_last_direct_kernel.argtypes = []
+    lib.dfdm_last_direct_kernel.restype = C.c_char_p
     lib.dfdm_profile_enable.argtypes = [i32]
     lib.dfdm_profile_enable.restype = None
     lib.dfdm_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i64)]
@@ -131,6 +133,10 @@ def plan_array(handle, which):
 
 def launch_count():
     return int(lib.dfdm_launch_count())
+
+
+def last_direct_kernel():
+    return lib.dfdm_last_direct_kernel().decode()
 
 
 def last_pcg_iterations():

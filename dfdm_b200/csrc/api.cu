@@ -9,6 +9,7 @@ namespace dfdm {
 
 std::atomic<long long> g_launches{0};
 void last_pcg_iterations(int* fwd, int* adj);
+const char* last_direct_kernel();
 void profile_enable(int on);
 void profile_read(double* ms, long long* count);
 
@@ -227,6 +228,12 @@ static int arena_prepare(Plan::Arena& a, int64_t bytes) {
             DFDM_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
             a.stream[k] = st;
         }
+    for (int k = 0; k < 3; ++k)
+        if (!a.ev_end[k]) {
+            cudaEvent_t e = nullptr;
+            DFDM_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+            a.ev_end[k] = e;
+        }
     for (int k = 0; k < Plan::kHostChunksMax; ++k) {
         if (!a.ev_in[k]) {
             cudaEvent_t e = nullptr;
@@ -299,6 +306,8 @@ void dfdm_plan_destroy(dfdm_plan* plan) {
             if (a.ptr) cudaFree(a.ptr);
             for (void* st : a.stream)
                 if (st) cudaStreamDestroy(static_cast<cudaStream_t>(st));
+            for (void* e : a.ev_end)
+                if (e) cudaEventDestroy(static_cast<cudaEvent_t>(e));
             for (int k = 0; k < Plan::kHostChunksMax; ++k) {
                 if (a.ev_in[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_in[k]));
                 if (a.ev_done[k]) cudaEventDestroy(static_cast<cudaEvent_t>(a.ev_done[k]));
@@ -546,7 +555,13 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     }
     turn.unlock();
     // the arena is released (and may be reused by another thread) on return: nothing of this call may still be in flight
-    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+    // (waited for on blocking-sync events: this thread sleeps through its copies instead of spinning next to the thread
+    // whose call has the kernels and is feeding the device)
+    auto drain = [&](cudaStream_t s, void* ev) -> cudaError_t {
+        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(ev), s);
+        return e != cudaSuccess ? e : cudaEventSynchronize(static_cast<cudaEvent_t>(ev));
+    };
+    cudaError_t e1 = drain(s_in, A.ev_end[0]), e2 = drain(s_cmp, A.ev_end[1]), e3 = drain(s_out, A.ev_end[2]);
     if (rc) return rc;
     DFDM_CUDA_OK(e1);
     DFDM_CUDA_OK(e2);
@@ -569,6 +584,8 @@ int dfdm_loss_and_grad_host(const dfdm_plan* plan, const dfdm_goalprog* prog, in
     }
     return host_eval(plan, prog, batch, q, loads, xyz_fixed, loss, dq, nullptr, nullptr, nullptr, nullptr, nullptr, status, options);
 }
+
+const char* dfdm_last_direct_kernel(void) { return last_direct_kernel(); }
 
 int64_t dfdm_launch_count(void) { return (int64_t)g_launches.load(); }
 

@@ -791,6 +791,9 @@ static int64_t global_band_stride(int nf, int w) {
     return (((int64_t)(w + 1) * direct_ld(nf, false) + 3 * (int64_t)nf) + 31) & ~(int64_t)31;
 }
 
+static thread_local const char* g_last_direct = "";
+const char* last_direct_kernel() { return g_last_direct; }
+
 int64_t direct_workspace(const Plan& P, int B, bool adjoint, bool has_prog) {
     (void)has_prog;
     Bump bump(nullptr);
@@ -890,6 +893,7 @@ int run_direct(Eval& ev) {
         const int grid = (int)std::min<int64_t>(std::min<int64_t>(B, kGlobalSlots), (int64_t)sms * per_sm);
         k_direct_global<<<grid, nt, (size_t)smem, ev.stream>>>(a);
         DFDM_LAUNCH_OK("k_direct_global");
+        g_last_direct = "k_direct_global";
         return DFDM_OK;
     }
     // ---- one warp per design: narrow bands whose factor leaves room for several designs per SM ------------------------
@@ -923,6 +927,7 @@ int run_direct(Eval& ev) {
             const int grid = (int)std::min<int64_t>(B, (int64_t)sms * per_sm);
             k_direct_team<<<grid, nt, smem, ev.stream>>>(a);
             DFDM_LAUNCH_OK("k_direct_team");
+            g_last_direct = "k_direct_team";
             return DFDM_OK;
         }
         // designs per CTA: up to 8 warps, as many as fit ~100 KB so that two CTAs share an SM; fewer when the batch is small
@@ -944,6 +949,7 @@ int run_direct(Eval& ev) {
         const int grid = (int)std::min<int64_t>(ctas, (int64_t)sms * per_sm);
         k_direct_warp<<<grid, warps * 32, smem, ev.stream>>>(a, (int)per_design);
         DFDM_LAUNCH_OK("k_direct_warp");
+        g_last_direct = "k_direct_warp";
         return DFDM_OK;
     }
     int nt = w <= 6 ? 32 : (w <= 12 ? 64 : (w <= 48 ? 128 : 256));
@@ -985,6 +991,7 @@ int run_direct(Eval& ev) {
     int grid = (int)std::min<int64_t>(B, (int64_t)sms * per_sm);
     kernel<<<grid, nt, (size_t)smem, ev.stream>>>(a);
     DFDM_LAUNCH_OK("k_direct_eval");
+    g_last_direct = nt > 256 ? "k_direct_chain" : "k_direct_eval";
     return DFDM_OK;
 }
 

@@ -62,6 +62,9 @@ struct PcgScalars {
                          // read [1 + par] (written during iteration k-1) and the direction kernel writes [1 + (par ^ 1)], so no
                          // kernel ever reads a snapshot that a concurrently running CTA may be writing
     int par;
+    unsigned long long* host_ring;   // pinned HOST memory, [4]: the direction kernel of iteration k (1-based) stores (k << 32 | columns
+                                     // still active) at [k & 3] straight over PCIe - the host follows convergence without a copy-engine
+                                     // transfer (which would queue behind the bulk copies of another host call's results) or an event
     int32_t* tickets;    // [nchunks]
     double* partial;     // [nslabs][NV][B] scratch for block partials
 };
@@ -534,10 +537,24 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
 // x += alpha p ; p = z + beta p   (z = r / diag for Jacobi, the V-cycle output for multigrid)
 __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                               const double* __restrict__ r, const float* __restrict__ z,
-                                                              double* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd) {
+                                                              double* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd, int tag) {
     pdl_wait();
-    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) S.n_active[1 + (S.par ^ 1)] = __ldcg(&S.n_active[0]);
+    const bool herald = blockIdx.x == 0 && threadIdx.x == 0;
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) {             // enqueued past convergence: nothing to do but to say so
+        if (herald && tag > 0 && S.host_ring) {
+            *reinterpret_cast<volatile unsigned long long*>(S.host_ring + (tag & 3)) = (unsigned long long)tag << 32;
+            __threadfence_system();
+        }
+        return;
+    }
+    if (herald) {
+        const int live_now = __ldcg(&S.n_active[0]);
+        S.n_active[1 + (S.par ^ 1)] = live_now;
+        if (tag > 0 && S.host_ring) {
+            *reinterpret_cast<volatile unsigned long long*>(S.host_ring + (tag & 3)) = ((unsigned long long)tag << 32) | (unsigned)live_now;
+            __threadfence_system();
+        }
+    }
     VEC_SETUP();
     if (!live) return;
     const double be = __ldcg(&S.beta[c * B + b]);
@@ -2573,6 +2590,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
     w.S.par = 0;
+    for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(w.S.host_ring)[k] = 0;   // no kernel of a previous solve is in flight
     k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0, keep);
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used = 0;
@@ -2580,10 +2598,11 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
         int rc = mg_vcycle(P, *M, base, B, w, 1, st, used, mp, over_w, w_levels);   // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
         DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
-                                                                                   w.S, 0));
+                                                                                   w.S, 0, 0));
         DFDM_LAUNCH_OK("k_pcg_direction");
         w.S.par ^= 1;
     }
+    int it = 0;
     auto iteration = [&]() -> int {
         if (matrix_free)
             DFDM_CUDA_OK(launch_chain(k_pcg_spmv_mf, cfg_mf.nchunks * cfg_mf.nslabs, kThreads, 0, st, P, cfg_mf, B, w.qT, w.p, w.Ap, w.S));
@@ -2601,13 +2620,12 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             prof_mark(st, -1, used);
         }
         DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r,
-                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1));
+                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1, it + 1));
         DFDM_LAUNCH_OK("k_pcg_direction");
         prof_mark(st, 2, used);
         w.S.par ^= 1;
         return DFDM_OK;
     };
-    int it = 0;
     if (every > 0) {
         // blocking polls: the host waits for the device every `every` iterations
         while (it < maxiter) {
@@ -2626,26 +2644,37 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
         *iters_out = it;
         return DFDM_OK;
     }
-    // look-ahead polls: the counter of every iteration is copied to pinned memory behind it; the host enqueues
-    // iteration k only after iteration k - kAhead has completed and shown unconverged columns.  The device always has
-    // work queued, nothing is rounded up to a polling interval, and the kAhead iterations enqueued past convergence
-    // exit at their first instruction (every kernel tests the counter snapshot of the previous iteration).
-    constexpr int kAhead = 2, kSlots = 4;
-    struct Events { cudaEvent_t e[kSlots] = {nullptr, nullptr, nullptr, nullptr}; };
-    static thread_local std::map<int, Events> per_device;              // events belong to the device they were created on
-    int dev = 0;
-    DFDM_CUDA_OK(cudaGetDevice(&dev));
-    cudaEvent_t* done = per_device[dev].e;
-    for (int k = 0; k < kSlots; ++k)
-        if (!done[k]) DFDM_CUDA_OK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
-    int32_t* flags = host_flag + 1;                                    // host_flag[0] is the verdict the caller reads
+    // look-ahead polls: the direction kernel of every iteration stores (iteration, columns still active) into a ring of
+    // pinned host words (PcgScalars::host_ring); the host enqueues iteration k only after iteration k - kAhead has
+    // reported unconverged columns.  The device always has work queued, nothing is rounded up to a polling interval, and
+    // the kAhead iterations enqueued past convergence exit at their first instruction (every kernel tests the counter
+    // snapshot of the previous iteration).  No copy-engine transfer and no event is involved: a 4-byte copy would queue
+    // behind the bulk result copies of another host call sharing the device (api.cu: host calls from several threads).
+    constexpr int kAhead = 2;
+    volatile unsigned long long* ring = w.S.host_ring;
     used = 0;
     prof_mark(st, -1, used);
     int converged_at = -1, checked = 0;
     std::vector<size_t> mark_at;                                       // profiling: first event of every iteration
     auto check = [&](int k) -> int {                                   // has iteration k (0-based) left nothing active?
-        DFDM_CUDA_OK(cudaEventSynchronize(done[k % kSlots]));
-        if (flags[k % kSlots] == 0 && converged_at < 0) converged_at = k + 1;
+        const unsigned long long want = (unsigned long long)k + 1;
+        unsigned long long v = ring[want & 3];
+        for (unsigned spins = 1; (v >> 32) != want; ++spins) {
+            if ((spins & 0x3ffff) == 0) {                              // now and then: is the stream still alive?
+                cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaErrorNotReady) {
+                    DFDM_CUDA_OK(q);
+                    v = ring[want & 3];                                // the stream has drained: the word is there, or never will be
+                    if ((v >> 32) != want) {
+                        set_error("PCG: iteration " + std::to_string(k) + " never reported its convergence counter");
+                        return DFDM_ECUDA;
+                    }
+                    break;
+                }
+            }
+            v = ring[want & 3];
+        }
+        if ((uint32_t)v == 0 && converged_at < 0) converged_at = k + 1;
         return DFDM_OK;
     };
     while (it < maxiter && converged_at < 0) {
@@ -2657,9 +2686,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
         mark_at.push_back(used);
         int rc = iteration();
         if (rc) return rc;
-        DFDM_CUDA_OK(cudaMemcpyAsync(&flags[it % kSlots], w.S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        DFDM_CUDA_OK(cudaEventRecord(done[it % kSlots], st));
-        prof_mark(st, -1, used);                                       // the 4-byte copy is not part of the next kernel's interval
+        prof_mark(st, -1, used);
         ++it;
     }
     for (; checked < it && converged_at < 0; ++checked) {
@@ -2709,7 +2736,8 @@ int run_pcg(Eval& ev) {
         return DFDM_ENOMEM;
     }
     static thread_local int32_t* host_flag = nullptr;
-    if (!host_flag) DFDM_CUDA_OK(cudaMallocHost(&host_flag, 64));
+    if (!host_flag) DFDM_CUDA_OK(cudaMallocHost(&host_flag, 64));       // [0]: verdict of a solve; bytes 32 .. 63: PcgScalars::host_ring
+    w.S.host_ring = reinterpret_cast<unsigned long long*>(host_flag + 8);
     const int grid = cfg.nchunks * cfg.nslabs;
     const int tb = 128, gb = (B + tb - 1) / tb;
 

@@ -140,6 +140,7 @@ struct Plan {
         void* stream[3] = {nullptr, nullptr, nullptr};
         void* ev_in[kHostChunksMax] = {nullptr};
         void* ev_done[kHostChunksMax] = {nullptr};
+        void* ev_end[3] = {nullptr, nullptr, nullptr};   // blocking-sync events: the end-of-call wait sleeps instead of spinning
     };
     struct ArenaSet { Arena slot[kArenaSlots]; };
     mutable std::map<int, ArenaSet> arena;

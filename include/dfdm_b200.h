@@ -255,6 +255,9 @@ DFDM_API int dfdm_loss_and_grad_host(const dfdm_plan* plan, const dfdm_goalprog*
 DFDM_API int64_t dfdm_launch_count(void);
 /* PCG iterations used by the most recent evaluation on this thread (forward solve, adjoint solve) */
 DFDM_API void dfdm_last_pcg_iterations(int32_t* forward_iters, int32_t* adjoint_iters);
+/* name of the kernel the most recent direct-path evaluation on this thread launched ("k_direct_warp", "k_direct_team",
+   "k_direct_chain", "k_direct_eval", "k_direct_global"; "" before the first): which launch shape a plan and batch got */
+DFDM_API const char* dfdm_last_direct_kernel(void);
 
 /*
  * Per-kernel timing of the PCG loop for roofline accounting: when enabled, a CUDA event is recorded on
