@@ -383,7 +383,7 @@ def gpu_arm(args, rank, world, local_rank):
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world, "n_nodes": plan.n,
                        "n_edges": E, "n_free": nf, "nnz": nnz, "solver": solver, "loss": wl["loss"],
                        "pcg_iterations": {"forward": iters[0], "adjoint": iters[1]},
-                       "pcg_rtol": args.pcg_rtol or _lib.PCG_RTOL_DEFAULT, "pcg_rtol_adjoint": args.pcg_rtol_adjoint or _lib.PCG_RTOL_ADJOINT_DEFAULT,
+                       "pcg_rtol": args.pcg_rtol or _lib.PCG_RTOL_DEFAULT, "pcg_rtol_adjoint": args.pcg_rtol_adjoint or (_lib.PCG_RTOL_ADJOINT_DEFAULT if (plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi") else _lib.PCG_RTOL_ADJOINT_JACOBI),
                        "pcg_rtol_note": "stop tests calibrated against SuperLU / the dense oracle with a tenfold margin to the 1e-9 / 1e-7 contract (include/dfdm_b200.h, tools/rtol_sweep.py)",
                        "preconditioner": ("aggregation multigrid, %d levels, %s" % (plan.info.get("mg_levels", 0) + 1, "V-cycle" if args.mg_w_levels < 0 else "W-cycle on the first %d coarse levels" % (args.mg_w_levels or 3))) if (solver == "pcg" and args.precond != "jacobi" and plan.info.get("mg_levels", 0) > 0) else ("jacobi" if solver == "pcg" else None),
                        "parallelism": "dp%d (designs sharded; exchange per step: %s)" % (world, sharded.collective if world > 1 else "none"),
@@ -403,13 +403,14 @@ def gpu_arm(args, rank, world, local_rank):
     elif solver == "pcg":
         nc = plan.info.get("mg_n_coarse", 0)
         is_mg = plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi"
-        # update: r in/out, Ap (+ 1/diag for Jacobi); direction: p in/out, x in/out, z (float) or r + 1/diag
-        alg = {"k_pcg_spmv": ((8.0 * E if args.spmv_matrix_free else 8.0 * nnz) + 48.0 * nf) * batch, "k_pcg_update": (72.0 if is_mg else 80.0) * nf * batch,
-               "k_pcg_direction": (108.0 if is_mg else 128.0) * nf * batch,
-               # single-precision V-cycle: K D^-1 (4 nnz), r in double (24 nf), t out (12 nf), coarse rhs out (12 nc)
-               "k_mg_down[level 0]": (4.0 * nnz + 36.0 * nf + 12.0 * nc) * batch,
-               # K (4 nnz), r (24 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
-               "k_mg_up[level 0]": (4.0 * nnz + 52.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
+        # spmv: K (8 nnz), p in single precision (12 nf), Ap out (24 nf); update: r in/out, Ap (+ the single-precision copy of r the
+        # cycle reads, or 1/diag for Jacobi); direction: x in/out (48 nf), p in/out (24 nf), z (float) or r + 1/diag
+        alg = {"k_pcg_spmv": ((8.0 * E if args.spmv_matrix_free else 8.0 * nnz) + 36.0 * nf) * batch, "k_pcg_update": (84.0 if is_mg else 80.0) * nf * batch,
+               "k_pcg_direction": (84.0 if is_mg else 104.0) * nf * batch,
+               # single-precision V-cycle: K D^-1 (4 nnz), r (12 nf), t out (12 nf), coarse rhs out (12 nc)
+               "k_mg_down[level 0]": (4.0 * nnz + 24.0 * nf + 12.0 * nc) * batch,
+               # K (4 nnz), r (12 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
+               "k_mg_up[level 0]": (4.0 * nnz + 40.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
         if is_mg:
             alg["multigrid coarse levels (per V-cycle)"] = coarse_cycle_bytes(plan, args.mg_w_levels) * batch
         alg["k_assemble"] = (8.0 * E + 8.0 * nnz + 32.0 * nf) * batch      # q in; K values, 1/diag, b (3 columns) out
@@ -427,12 +428,12 @@ def gpu_arm(args, rank, world, local_rank):
         it_ms = sum(kk["avg_ms"] for kk in per_iteration)
         it_bytes = sum(kk["algorithmic_bytes"] for kk in per_iteration)
         # the WHOLE step against the roofline: algorithmic bytes of everything a step launches / ms_per_step of the
-        # un-instrumented region.  Per solve: k_pcg_init (r, 1/diag in; x, p out: 80 n_f), one preconditioner cycle and
-        # one direction pass without the x update (60 n_f) before the first iteration, then the iterations.
+        # un-instrumented region.  Per solve: k_pcg_init (r, 1/diag in; x, p, single-precision r out: 80 n_f), one preconditioner
+        # cycle and one direction pass without the x update (36 n_f) before the first iteration, then the iterations.
         n_iter = iters[0] + iters[1]
         cyc = alg["k_mg_down[level 0]"] + alg["k_mg_up[level 0]"] + alg["multigrid coarse levels (per V-cycle)"] if is_mg else 0.0
         step_parts = {"pcg iterations (%d forward + %d adjoint)" % iters: n_iter * it_bytes,
-                      "solver start (init, first cycle, first direction) x 2": 2 * (80.0 * nf * batch + cyc + 60.0 * nf * batch),
+                      "solver start (init, first cycle, first direction) x 2": 2 * (80.0 * nf * batch + cyc + 36.0 * nf * batch),
                       "k_assemble": alg["k_assemble"], "state, loss and reverse edge kernels": alg["state, loss and reverse edge kernels (5 launches)"],
                       "hierarchy set-up (single-precision copies, Galerkin sums)": mg_setup_bytes(plan) * batch if is_mg else 0.0,
                       "k_edge_dq": (40.0 * E + 24.0 * plan.n) * batch, "layout changes of q and dq": 32.0 * E * batch}

@@ -25,7 +25,7 @@ ARR_NODE_INC_PTR, ARR_NODE_INC_EDGE, ARR_NODE_INC_SIGN = 7, 8, 9
 ARR_MG_ROWS, ARR_MG_NNZ, ARR_PCG_PERM, ARR_MG_AGG = 10, 11, 12, 100
 FLAG_SPMV_MATRIX_FREE = 1
 FLAG_MG_NO_TAIL = 2
-PCG_RTOL_DEFAULT, PCG_RTOL_ADJOINT_DEFAULT = 1e-12, 5e-9     # include/dfdm_b200.h DFDM_PCG_RTOL_*_DEFAULT
+PCG_RTOL_DEFAULT, PCG_RTOL_ADJOINT_DEFAULT, PCG_RTOL_ADJOINT_JACOBI = 1e-12, 5e-9, 5e-10     # include/dfdm_b200.h DFDM_PCG_RTOL_*
 
 GOAL_KINDS = {"NodePoint": 0, "NodeLine": 1, "NodePlane": 2, "NodeResidualForce": 3, "NodeResidualVector": 4,
               "NodeResidualDirection": 5, "EdgeLength": 6, "EdgeForce": 7, "EdgeLoadPath": 8, "EdgeVectorAngle": 9,

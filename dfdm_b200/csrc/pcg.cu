@@ -286,10 +286,17 @@ __device__ bool publish_vec(const double (&v)[NV], const LaneCfg& cfg, int B, do
     return s_last != 0;
 }
 
+// The search direction p is STORED in single precision.  What CG needs to stay exact is that x and r move by the same
+// vector: x += alpha p and r -= alpha (K p) both use p as stored, K p and every dot product are formed in double precision,
+// so r remains the true residual of x to double-precision rounding.  Rounding p itself (6e-8 relative) only tilts the
+// direction, like an inexact preconditioner: same iteration counts, same answers (tools/proto/p32_check.py), and
+// 36 n_f bytes less per iteration and design (the gathers of the SpMV move 4-byte words).
+typedef float pvec;
+
 // x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
-                                                         const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
-                                                         PcgScalars S, int mg, const int32_t* __restrict__ keep) {
+                                                         const double* __restrict__ r, double* __restrict__ x, pvec* __restrict__ p,
+                                                         float* __restrict__ r32, PcgScalars S, int mg, const int32_t* __restrict__ keep) {
     // keep (fallback run only): columns that the previous attempt converged stay frozen and keep their solution
     VEC_SETUP();
     double v[2] = {0, 0};
@@ -300,7 +307,8 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
             double rc = r[o];
             double z = rc * dinv[(size_t)f * B + b];
             if (!kept) x[o] = 0.0;
-            p[o] = mg ? 0.0 : z;             // multigrid: the first direction comes from the V-cycle
+            p[o] = mg ? (pvec)0 : (pvec)z;   // multigrid: the first direction comes from the V-cycle
+            if (r32) r32[o] = (float)rc;
             v[0] += rc * z;
             v[1] += rc * rc;
         }
@@ -352,7 +360,7 @@ constexpr int kVecUnroll = DFDM_VEC_UNROLL;
 // All loads of a batch of row entries are issued before their first use.
 __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(PlanDev P, LaneCfg cfg, int B,
                                                                           const double* __restrict__ vals,
-                                                                          const double* __restrict__ p, double* __restrict__ Ap,
+                                                                          const pvec* __restrict__ p, double* __restrict__ Ap,
                                                                           PcgScalars S) {
     pdl_wait();
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
@@ -361,18 +369,19 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
     if (live) {
         const int W = P.ell_w;
         const size_t sB = (size_t)B;
-        const double* pb = p + b;
+        const pvec* pb = p + b;
         const double* vb = vals + b;
         TILE_ROWS(f, P.nf) {
             const int k0 = P.rowptr[f], k1 = P.rowptr[f + 1];
             int col[kSpmvBatch];
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
-            double a[kSpmvBatch], x0[kSpmvBatch], x1[kSpmvBatch], x2[kSpmvBatch];
+            double a[kSpmvBatch];
+            pvec x0[kSpmvBatch], x1[kSpmvBatch], x2[kSpmvBatch];
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) {
                 a[u] = k0 + u < k1 ? vb[(size_t)(k0 + u) * sB] : 0.0;
-                const double* pj = pb + (size_t)col[u] * 3 * sB;
+                const pvec* pj = pb + (size_t)col[u] * 3 * sB;
                 x0[u] = pj[0];
                 x1[u] = pj[sB];
                 x2[u] = pj[2 * sB];
@@ -382,16 +391,16 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
             double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
             for (int u = 0; u < kSpmvBatch; ++u) {
-                a0 += a[u] * x0[u];
-                a1 += a[u] * x1[u];
-                a2 += a[u] * x2[u];
+                a0 += a[u] * (double)x0[u];
+                a1 += a[u] * (double)x1[u];
+                a2 += a[u] * (double)x2[u];
             }
             for (int k = k0 + kSpmvBatch; k < k1; ++k) {          // rows wider than one batch
                 double ak = vb[(size_t)k * sB];
-                const double* pj = pb + (size_t)P.colidx[k] * 3 * sB;
-                a0 += ak * pj[0];
-                a1 += ak * pj[sB];
-                a2 += ak * pj[2 * sB];
+                const pvec* pj = pb + (size_t)P.colidx[k] * 3 * sB;
+                a0 += ak * (double)pj[0];
+                a1 += ak * (double)pj[sB];
+                a2 += ak * (double)pj[2 * sB];
             }
             Ap[od] = a0;
             Ap[od + sB] = a1;
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
 // time out of cache) instead of the CSR values (8 nnz): 1.06 instead of 2.61 MB per design on the 258 x 258 grid.
 __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(PlanDev P, LaneCfg cfg, int B,
                                                                              const double* __restrict__ qT,
-                                                                             const double* __restrict__ p, double* __restrict__ Ap,
+                                                                             const pvec* __restrict__ p, double* __restrict__ Ap,
                                                                              PcgScalars S) {
     pdl_wait();
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(P
         constexpr int U = 4;
         const int W = P.inc_w;
         const size_t sB = (size_t)B;
-        const double* pb = p + b;
+        const pvec* pb = p + b;
         const double* qb = qT + b;
         TILE_ROWS(f, P.nf) {
             const int cnt = P.finc_ptr[f + 1] - P.finc_ptr[f];
@@ -444,11 +453,12 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(P
                     e[u] = u0 + u < cnt ? P.inc_edge[at] : -1;
                     col[u] = u0 + u < cnt ? P.inc_col[at] : -1;
                 }
-                double q[U], x0[U], x1[U], x2[U];
+                double q[U];
+                pvec x0[U], x1[U], x2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     q[u] = e[u] >= 0 ? qb[(size_t)e[u] * sB] : 0.0;
-                    const double* pj = pb + (size_t)(col[u] >= 0 ? col[u] : f) * 3 * sB;
+                    const pvec* pj = pb + (size_t)(col[u] >= 0 ? col[u] : f) * 3 * sB;
                     x0[u] = pj[0];
                     x1[u] = pj[sB];
                     x2[u] = pj[2 * sB];
@@ -457,9 +467,9 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(P
                 for (int u = 0; u < U; ++u) {
                     diag += q[u];
                     const double qo = col[u] >= 0 ? q[u] : 0.0;
-                    s0 += qo * x0[u];
-                    s1 += qo * x1[u];
-                    s2 += qo * x2[u];
+                    s0 += qo * (double)x0[u];
+                    s1 += qo * (double)x1[u];
+                    s2 += qo * (double)x2[u];
                 }
             }
             const double a0 = diag * d0 - s0, a1 = diag * d1 - s1, a2 = diag * d2 - s2;
@@ -484,12 +494,14 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(P
     }
 }
 
-// r -= alpha Ap ; rr = r.r ; Jacobi: rho' = r . (r/diag), beta = rho'/rho ; convergence
+// r -= alpha Ap ; rr = r.r ; Jacobi: rho' = r . (r/diag), beta = rho'/rho ; convergence.  Multigrid: also a single-precision
+// copy of r - the cycle rounds r to single precision on its way in anyway (twice on level 0: down and up pass), so it
+// reads 12 instead of 24 bytes per row and coordinate each time, and the neighbour gathers of the down pass move 4-byte words
 // (x += alpha p lives in the direction kernel, which reads p anyway)
 __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(int nf, LaneCfg cfg, int B,
                                                                               const double* __restrict__ dinv,
                                                                               const double* __restrict__ Ap, double* __restrict__ r,
-                                                                              PcgScalars S, double tol2, int mg) {
+                                                                              float* __restrict__ r32, PcgScalars S, double tol2, int mg) {
     pdl_wait();
     // the snapshot cannot change while this kernel runs, so either every CTA takes its ticket or none does
     if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
@@ -502,6 +514,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
             size_t o = ((size_t)f * 3 + c) * B + b;
             double rc = r[o] - al * Ap[o];
             r[o] = rc;
+            if (r32) r32[o] = (float)rc;        // what the multigrid cycle reads: it works in single precision throughout
             if (!mg) v[0] += rc * rc * dinv[(size_t)f * B + b];
             v[1] += rc * rc;
         }
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
 // x += alpha p ; p = z + beta p   (z = r / diag for Jacobi, the V-cycle output for multigrid)
 __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                               const double* __restrict__ r, const float* __restrict__ z,
-                                                              double* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd, int tag) {
+                                                              pvec* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd, int tag) {
     pdl_wait();
     const bool herald = blockIdx.x == 0 && threadIdx.x == 0;
     if (__ldcg(&S.n_active[1 + S.par]) == 0) {             // enqueued past convergence: nothing to do but to say so
@@ -562,10 +575,10 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_directi
 #pragma unroll(kVecUnroll)
     for (int f = row0; f < nf; f += rstride) {
         size_t o = ((size_t)f * 3 + c) * B + b;
-        double pc = p[o];
+        double pc = (double)p[o];
         if (xupd) x[o] += al * pc;
         double zc = z ? (double)z[o] : r[o] * dinv[(size_t)f * B + b];
-        p[o] = zc + be * pc;
+        p[o] = (pvec)(zc + be * pc);
     }
 }
 
@@ -1959,7 +1972,9 @@ struct MgBuffers {
 
 struct PcgBuffers {
     MgBuffers mg;
-    double *qT, *vals, *dinv, *xs, *r, *p, *Ap;
+    double *qT, *vals, *dinv, *xs, *r, *Ap;
+    float* r32;            // r rounded to single precision: the right-hand side of the multigrid cycle
+    pvec* p;               // search direction (single precision: see the typedef)
     int32_t* keep;         // [3][B] columns converged by the multigrid attempt (Jacobi fallback only)
     double *X, *R, *U, *L, *F, *Xb, *Rb, *Ub, *dqT;
     double *cX, *cR, *cU, *cL, *cF;
@@ -2014,7 +2029,8 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
     w.dinv = bump.take<double>(nf * B);
     w.xs = bump.take<double>(nf * 3 * B);
     w.r = bump.take<double>(nf * 3 * B);
-    w.p = bump.take<double>(nf * 3 * B);
+    w.p = bump.take<pvec>(nf * 3 * B);
+    w.r32 = bump.take<float>(nf * 3 * B);
     w.Ap = bump.take<double>(nf * 3 * B);
     w.keep = bump.take<int32_t>(3 * B);
     w.X = bump.take<double>(n * 3 * B);
@@ -2515,17 +2531,17 @@ static int mg_vcycle_v(const PlanDev& P, const MgDev& M, int B, PcgBuffers& w, i
     MgCtx c{&P, &M, &w, B, st, mpw, mp, vec_base(B, V), w_levels, bottom, tail};
     w.mg.t[0] = reinterpret_cast<mgf*>(w.Ap);           // Ap is dead between the update and the next SpMV
     MgMat A = mg_mat(P, M, w, 0);
-    LaneCfg cd = rows_cfg(k_mg_down<double, V>, c.vbase, M.lv[0].n, down_tiles);
-    DFDM_CUDA_OK(launch_chain(k_mg_down<double, V>, cd.nchunks * cd.nslabs, kThreads, 0, st, A, M.lv[0], cd, B, w.r, w.mg.t[0], w.mg.b[1],
+    LaneCfg cd = rows_cfg(k_mg_down<float, V>, c.vbase, M.lv[0].n, down_tiles);
+    DFDM_CUDA_OK(launch_chain(k_mg_down<float, V>, cd.nchunks * cd.nslabs, kThreads, 0, st, A, M.lv[0], cd, B, (const float*)w.r32, w.mg.t[0], w.mg.b[1],
                                                                      w.S.n_active + w.S.par, mp));
     DFDM_LAUNCH_OK("k_mg_down");
     prof_mark(st, 3, used);
     int rc = mg_solve_level<V>(c, 1, w.mg.b[1], w.mg.z[1]);
     if (rc) return rc;
     prof_mark(st, 5, used);                              // everything below the finest level, per cycle
-    LaneCfg cu = rows_cfg(k_mg_up<double, V, false>, c.vbase, A.n, up_tiles);
+    LaneCfg cu = rows_cfg(k_mg_up<float, V, false>, c.vbase, A.n, up_tiles);
     const MgParams mp0 = w_levels > 0 ? mpw : mp;     // level 1 is solved twice whenever there is a W level
-    DFDM_CUDA_OK(launch_chain(k_mg_up<double, V, false>, cu.nchunks * cu.nslabs, kThreads, 0, st, A, M.lv[0], cu, B, w.r, w.mg.t[0], w.mg.z[1], w.mg.z[0],
+    DFDM_CUDA_OK(launch_chain(k_mg_up<float, V, false>, cu.nchunks * cu.nslabs, kThreads, 0, st, A, M.lv[0], cu, B, (const float*)w.r32, w.mg.t[0], w.mg.z[1], w.mg.z[0],
                                                                           w.S, 1, first, mp0));
     DFDM_LAUNCH_OK("k_mg_up");
     prof_mark(st, 4, used);
@@ -2591,7 +2607,7 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
     w.S.par = 0;
     for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(w.S.host_ring)[k] = 0;   // no kernel of a previous solve is in flight
-    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, w.S, mg ? 1 : 0, keep);
+    k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, mg ? w.r32 : nullptr, w.S, mg ? 1 : 0, keep);
     DFDM_LAUNCH_OK("k_pcg_init");
     size_t used = 0;
     if (mg) {
@@ -2610,8 +2626,8 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S));
         DFDM_LAUNCH_OK("k_pcg_spmv");
         prof_mark(st, 0, used);
-        DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r, w.S, rtol * rtol,
-                                                                                mg ? 1 : 0));
+        DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r,
+                                                                                mg ? w.r32 : (float*)nullptr, w.S, rtol * rtol, mg ? 1 : 0));
         DFDM_LAUNCH_OK("k_pcg_update");
         prof_mark(st, 1, used);
         if (mg) {
@@ -2761,7 +2777,7 @@ int run_pcg(Eval& ev) {
         if (rc) return rc;
     }
     const double rtol_fwd = ev.opt.pcg_rtol > 0 ? ev.opt.pcg_rtol : DFDM_PCG_RTOL_DEFAULT;
-    const double rtol_adj = ev.opt.pcg_rtol_adjoint > 0 ? ev.opt.pcg_rtol_adjoint : DFDM_PCG_RTOL_ADJOINT_DEFAULT;
+    const double rtol_adj = ev.opt.pcg_rtol_adjoint > 0 ? ev.opt.pcg_rtol_adjoint : (use_mg ? DFDM_PCG_RTOL_ADJOINT_DEFAULT : DFDM_PCG_RTOL_ADJOINT_JACOBI);
     rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, rtol_fwd, st, host_flag, &g_iters[0], [&]() -> int {
         k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
         DFDM_LAUNCH_OK("k_assemble");
