@@ -555,9 +555,12 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     }
     turn.unlock();
     // the arena is released (and may be reused by another thread) on return: nothing of this call may still be in flight
-    // (waited for on blocking-sync events: this thread sleeps through its copies instead of spinning next to the thread
-    // whose call has the kernels and is feeding the device)
+    // A PCG call lasts tens of milliseconds: it waits on blocking-sync events, so that this thread sleeps through its copies
+    // instead of spinning next to the thread whose call has the kernels and is feeding the device.  A direct-path call is
+    // a sub-millisecond kernel: waking up would cost as much as the kernel, so it spins (cudaStreamSynchronize).
+    const bool sleepy = solver == DFDM_SOLVER_PCG;
     auto drain = [&](cudaStream_t s, void* ev) -> cudaError_t {
+        if (!sleepy) return cudaStreamSynchronize(s);
         cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(ev), s);
         return e != cudaSuccess ? e : cudaEventSynchronize(static_cast<cudaEvent_t>(ev));
     };

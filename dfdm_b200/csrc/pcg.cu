@@ -2777,7 +2777,10 @@ int run_pcg(Eval& ev) {
         if (rc) return rc;
     }
     const double rtol_fwd = ev.opt.pcg_rtol > 0 ? ev.opt.pcg_rtol : DFDM_PCG_RTOL_DEFAULT;
-    const double rtol_adj = ev.opt.pcg_rtol_adjoint > 0 ? ev.opt.pcg_rtol_adjoint : (use_mg ? DFDM_PCG_RTOL_ADJOINT_DEFAULT : DFDM_PCG_RTOL_ADJOINT_JACOBI);
+    // DFDM_PCG_RTOL_ADJOINT_MG: calibration runs only (the parity suite at tenfold-tightened tolerances against candidate defaults)
+    static const double adj_mg_env = std::getenv("DFDM_PCG_RTOL_ADJOINT_MG") ? std::atof(std::getenv("DFDM_PCG_RTOL_ADJOINT_MG")) : 0.0;
+    const double adj_mg = adj_mg_env > 0 ? adj_mg_env : DFDM_PCG_RTOL_ADJOINT_DEFAULT;
+    const double rtol_adj = ev.opt.pcg_rtol_adjoint > 0 ? ev.opt.pcg_rtol_adjoint : (use_mg ? adj_mg : DFDM_PCG_RTOL_ADJOINT_JACOBI);
     rc = pcg_solve(P, use_mg ? &ev.M : nullptr, cfg, B, w, ev.opt, rtol_fwd, st, host_flag, &g_iters[0], [&]() -> int {
         k_assemble<<<grid, kThreads, 0, st>>>(P, cfg, B, w.qT, ev.loads, ev.xfix, w.vals, w.dinv, w.r);
         DFDM_LAUNCH_OK("k_assemble");
