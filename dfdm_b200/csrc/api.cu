@@ -516,6 +516,10 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     layout(real);
     cudaStream_t s_in = static_cast<cudaStream_t>(A.stream[0]), s_cmp = static_cast<cudaStream_t>(A.stream[1]),
                  s_out = static_cast<cudaStream_t>(A.stream[2]);
+    // Everything that enqueues work sits in `enqueue`, so that an error on the way (reported through its return code) still
+    // reaches the drain below: the arena is released on return, and nothing of this call may be in flight by then.
+    std::unique_lock<std::mutex> turn(compute_turn(device), std::defer_lock);
+    auto enqueue = [&]() -> int {
     // way in: the design-independent arrays, then q chunk by chunk
     DFDM_CUDA_OK(cudaMemcpyAsync(d_loads, loads, sizeof(double) * n * 3, cudaMemcpyHostToDevice, s_in));
     if (nx > 0) DFDM_CUDA_OK(cudaMemcpyAsync(d_xfix, xyz_fixed, sizeof(double) * nx * 3, cudaMemcpyHostToDevice, s_in));
@@ -527,7 +531,8 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
     auto at = [](double* p, int64_t off) { return p ? p + off : nullptr; };
     // the kernels of this call, in its turn on the device; the copies above and the wait below stay outside the turn, so
     // another thread's call copies in while this one computes and computes while this one copies out
-    std::unique_lock<std::mutex> turn(compute_turn(device));
+    turn.lock();
+    int rc = DFDM_OK;
     for (int c = 0; c < nchunks && rc == DFDM_OK; ++c) {
         const int64_t b0 = cb[c], nb = cb[c + 1] - cb[c];
         DFDM_CUDA_OK(cudaStreamWaitEvent(s_cmp, static_cast<cudaEvent_t>(A.ev_in[c]), 0));
@@ -553,8 +558,10 @@ static int host_eval(const dfdm_plan* plan, const dfdm_goalprog* prog, int32_t B
             break;
         if (status) DFDM_CUDA_OK(cudaMemcpyAsync(status + b0, d_status + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
     }
-    turn.unlock();
-    // the arena is released (and may be reused by another thread) on return: nothing of this call may still be in flight
+    return rc;
+    };
+    rc = enqueue();
+    if (turn.owns_lock()) turn.unlock();
     // A PCG call lasts tens of milliseconds: it waits on blocking-sync events, so that this thread sleeps through its copies
     // instead of spinning next to the thread whose call has the kernels and is feeding the device.  A direct-path call is
     // a sub-millisecond kernel: waking up would cost as much as the kernel, so it spins (cudaStreamSynchronize).

@@ -296,26 +296,30 @@ class Evaluator:
         The library gives every call in flight an arena and streams of its own and lets the calls take turns with the
         kernels (include/dfdm_b200.h, host-buffer variants): one call's copies run under another call's kernels.
         Returns when every batch is back on the host."""
-        import threading
+        from concurrent.futures import ThreadPoolExecutor
         threads = max(1, min(int(threads), len(batches)))
         if threads == 1:
             for b in batches:
                 self.loss_and_grad_host(prog, *b)
             return
-        errors = []
+        # one long-lived worker thread per slot (the library keeps per-thread pinned words and events: threads are reused)
+        workers = getattr(self, "_host_workers", None)
+        if workers is None or len(workers) < threads:
+            for w in workers or ():
+                w.shutdown(wait=True)
+            workers = self._host_workers = [ThreadPoolExecutor(max_workers=1, thread_name_prefix="dfdm-host-%d" % t) for t in range(threads)]
 
         def work(t):
-            try:
-                for b in batches[t::threads]:
-                    self.loss_and_grad_host(prog, *b)
-            except BaseException as exc:                                 # handed to the caller below
-                errors.append(exc)
+            for b in batches[t::threads]:
+                self.loss_and_grad_host(prog, *b)
 
-        pool = [threading.Thread(target=work, args=(t,), name="dfdm-host-%d" % t) for t in range(threads)]
-        for th in pool:
-            th.start()
-        for th in pool:
-            th.join()
+        futures = [workers[t].submit(work, t) for t in range(threads)]
+        errors = []
+        for f in futures:
+            try:
+                f.result()
+            except BaseException as exc:                                 # wait for every slot before raising
+                errors.append(exc)
         if errors:
             raise errors[0]
 
