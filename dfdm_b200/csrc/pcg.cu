@@ -219,8 +219,11 @@ constexpr int kVecThreads = 384;
 // placed while kernel k drains; it then waits here, at its first instruction, until kernel k has completed and its
 // writes are visible.  That takes the launch latency out of the ~25 kernel boundaries of an iteration.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// (an early griddepcontrol.launch_dependents after the wait was measured: 1 % slower - the waiting CTAs of the next
-// kernel take issue slots from the tail of this one)
+// (an early griddepcontrol.launch_dependents after the wait, in every kernel, was measured: 1 % slower - the waiting CTAs
+// of the next kernel take issue slots from the tail of this one.  It pays where the next kernel has real work to do
+// before its wait: the down pass that precedes k_mg_tail releases it early (MgParams::early), and the tail kernel stages
+// its index tables and its design pair's operators - none of which the down pass writes - into shared memory meanwhile.)
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 static bool pdl_enabled() {
     static const bool on = !(std::getenv("DFDM_PDL") && std::atoi(std::getenv("DFDM_PDL")) == 0);
@@ -614,7 +617,7 @@ constexpr double kMgOmegaDefault = 0.8;
 constexpr double kMgOverDefault = 1.7;   // V-cycle
 constexpr double kMgOverW = 1.3;         // under a W-cycle, levels whose coarse problem is solved once: nested scalings multiply (1.7 diverges)
 constexpr double kMgOverTwice = 1.7;     // levels whose coarse problem is solved twice: two corrections combine to 1-(1-s)^2 <= 1, safe below 2
-struct MgParams { float omega, over; };
+struct MgParams { float omega, over; int early = 0; };   // early: let the next kernel of the chain start its preamble now
 
 // level 0: single-precision copies of K, K D^-1 and 1/diag from the assembled double-precision operator
 __global__ void __launch_bounds__(kThreads) k_mg_prepare0(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ell_col,
@@ -729,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_down(MgMat A, MgLevelDev L, 
                                                         mgf* __restrict__ t, mgf* __restrict__ b_coarse,
                                                         const int32_t* __restrict__ n_active, MgParams mp) {
     pdl_wait();
+    if (mp.early) pdl_release();
     if (__ldcg(&n_active[1]) == 0) return;
     LANE_SETUP_V();
     if (!live) return;
@@ -1419,14 +1423,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, 
         tail_stage(L.col, reinterpret_cast<uint16_t*>(tsm + L.s_col), L.ent);
         tail_stage(L.aggc, reinterpret_cast<uint16_t*>(tsm + L.s_aggc), L.ent);
     }
-    pdl_wait();
-    if (__ldcg(&n_active[1]) == 0) return;
-    const float omega = a.omega;
-    const size_t il_stride = (size_t)B / 2;                 // float2 elements between consecutive (row, coordinate) entries
-    int tr_n = 0;
-    TAIL_MARK(0);
-    for (int pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-        // ---- this pair's operators into shared memory -------------------------------------------------------------
+    // so are the operators of a design pair (repacked once per evaluation, long before this cycle): the first pair's too
+    auto stage_operators = [&](int pair) {
         for (int k = 0; k < last; ++k) {
             const TailLevel& L = a.L[k];
             tail_stage2(L.vals + (size_t)pair * L.ent, reinterpret_cast<float2*>(tsm + L.s_vals), L.ent);
@@ -1434,6 +1432,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_mg_tail(TailArgs a, int B, 
         }
         const int ncst = a.L[last].n;
         tail_stage2(a.inv + (size_t)pair * ncst * ncst, reinterpret_cast<float2*>(tsm + a.s_inv), ncst * ncst);
+    };
+    if ((int)blockIdx.x < pairs) stage_operators(blockIdx.x);
+    pdl_wait();
+    if (__ldcg(&n_active[1]) == 0) return;
+    const float omega = a.omega;
+    const size_t il_stride = (size_t)B / 2;                 // float2 elements between consecutive (row, coordinate) entries
+    int tr_n = 0;
+    TAIL_MARK(0);
+    for (int pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        // ---- this pair's operators into shared memory (the first pair's are there already) ------------------------
+        if (pair != (int)blockIdx.x) stage_operators(pair);
         const int n0 = a.L[0].n;
         float2* const S = reinterpret_cast<float2*>(tsm + a.L[0].s_b);      // staging buffer of the top level
         float2* const gb0 = a.L[0].gb + (size_t)pair * 3 * n0;
@@ -2321,9 +2330,12 @@ static int mg_cycle_level(const MgCtx& c, int l, const mgf* rhs, mgf* out, const
     PcgBuffers& w = *c.w;
     MgMat A = mg_mat(*c.P, M, w, l);
     const MgParams mp = l < c.w_levels ? c.mp : c.mp_single;
+    MgParams mpd = mp;
+    static const bool early_off = std::getenv("DFDM_TAIL_EARLY") && std::atoi(std::getenv("DFDM_TAIL_EARLY")) == 0;
+    mpd.early = (V == 2 && c.tail > 0 && l + 1 == c.tail && !early_off) ? 1 : 0;   // the tail kernel follows: it has a preamble worth starting
     LaneCfg cd = rows_cfg(k_mg_down<mgf, V>, c.vbase, M.lv[l].n);
     DFDM_CUDA_OK(launch_chain(k_mg_down<mgf, V>, cd.nchunks * cd.nslabs, kThreads, 0, c.st, A, M.lv[l], cd, c.B, rhs, w.mg.t[l], w.mg.b[l + 1],
-                                                                      w.S.n_active + w.S.par, mp));
+                                                                      w.S.n_active + w.S.par, mpd));
     DFDM_LAUNCH_OK("k_mg_down");
     int rc = mg_solve_level<V>(c, l + 1, w.mg.b[l + 1], w.mg.z[l + 1]);
     if (rc) return rc;
