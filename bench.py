@@ -404,9 +404,10 @@ def gpu_arm(args, rank, world, local_rank):
         nc = plan.info.get("mg_n_coarse", 0)
         is_mg = plan.info.get("mg_levels", 0) > 0 and args.precond != "jacobi"
         # spmv: K (8 nnz), p in single precision (12 nf), Ap out (24 nf); update: r in/out, Ap (+ the single-precision copy of r the
-        # cycle reads, or 1/diag for Jacobi); direction: x in/out (48 nf), p in/out (24 nf), z (float) or r + 1/diag
+        # cycle reads, or 1/diag for Jacobi); direction: p in, p out (12 nf each), z (float) or r + 1/diag, plus its share of
+        # k_pcg_xupdate, which adds a window of 8 iterations to x in one pass: (48 + 8 x 12) nf / 8 = 18 nf per iteration
         alg = {"k_pcg_spmv": ((8.0 * E if args.spmv_matrix_free else 8.0 * nnz) + 36.0 * nf) * batch, "k_pcg_update": (84.0 if is_mg else 80.0) * nf * batch,
-               "k_pcg_direction": (84.0 if is_mg else 104.0) * nf * batch,
+               "k_pcg_direction": (54.0 if is_mg else 74.0) * nf * batch,
                # single-precision V-cycle: K D^-1 (4 nnz), r (12 nf), t out (12 nf), coarse rhs out (12 nc)
                "k_mg_down[level 0]": (4.0 * nnz + 24.0 * nf + 12.0 * nc) * batch,
                # K (4 nnz), r (12 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
@@ -432,6 +433,7 @@ def gpu_arm(args, rank, world, local_rank):
         # cycle and one direction pass without the x update (36 n_f) before the first iteration, then the iterations.
         n_iter = iters[0] + iters[1]
         cyc = alg["k_mg_down[level 0]"] + alg["k_mg_up[level 0]"] + alg["multigrid coarse levels (per V-cycle)"] if is_mg else 0.0
+        # (the x passes at the end of each solve cover a partial window: a few n_f bytes more than the amortised share, not counted)
         step_parts = {"pcg iterations (%d forward + %d adjoint)" % iters: n_iter * it_bytes,
                       "solver start (init, first cycle, first direction) x 2": 2 * (80.0 * nf * batch + cyc + 36.0 * nf * batch),
                       "k_assemble": alg["k_assemble"], "state, loss and reverse edge kernels": alg["state, loss and reverse edge kernels (5 launches)"],

@@ -54,7 +54,7 @@ constexpr int kThreads = 256;
 // Per-design scalars of the solver, each [3][B] unless noted.
 struct PcgScalars {
     double* rho;      // r . z
-    double* alpha;
+    double* alpha;    // [kPRing][3][B]: the step lengths of the last kPRing iterations (the x update needs a window of them)
     double* beta;
     double* bb;       // ||b||^2
     int32_t* frozen;  // [3][B] != 0: alpha forced to 0.  1 converged (or zero right-hand side), 2 non-finite, 3 breakdown
@@ -62,6 +62,9 @@ struct PcgScalars {
                          // read [1 + par] (written during iteration k-1) and the direction kernel writes [1 + (par ^ 1)], so no
                          // kernel ever reads a snapshot that a concurrently running CTA may be writing
     int par;
+    int aslot;           // slot of the current iteration in the rings below (iteration % kPRing)
+    int32_t* exec_tag;   // [kPRing] iteration (1-based) whose direction kernel last ran with that slot: tells the x update which of
+                         // the iterations of its window actually executed (those enqueued past convergence exit at once)
     unsigned long long* host_ring;   // pinned HOST memory, [4]: the direction kernel of iteration k (1-based) stores (k << 32 | columns
                                      // still active) at [k & 3] straight over PCIe - the host follows convergence without a copy-engine
                                      // transfer (which would queue behind the bulk copies of another host call's results) or an event
@@ -296,6 +299,13 @@ __device__ bool publish_vec(const double (&v)[NV], const LaneCfg& cfg, int B, do
 // 36 n_f bytes less per iteration and design (the gathers of the SpMV move 4-byte words).
 typedef float pvec;
 
+// x is not needed before the solve ends, so x += alpha p is not done iteration by iteration (48 n_f bytes each time for
+// x in and out): the search directions of kXWindow consecutive iterations stay in a ring of kXWindow + 1 buffers (one more
+// for the direction being formed) with their step lengths, and ONE pass, k_pcg_xupdate, adds the whole window to x -
+// (48 + 12 kXWindow) n_f bytes per window instead of 48 kXWindow.
+constexpr int kXWindow = 8;
+constexpr int kPRing = kXWindow + 1;
+
 // x = 0, p = z = r / diag, rho = r.z, bb = r.r   (r holds the right-hand side on entry)
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                          const double* __restrict__ r, double* __restrict__ x, pvec* __restrict__ p,
@@ -354,7 +364,18 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init(int nf, LaneCfg cfg, i
 #ifndef DFDM_VEC_UNROLL
 #define DFDM_VEC_UNROLL 4
 #endif
+#ifndef DFDM_DIR_UNROLL
+#define DFDM_DIR_UNROLL 4
+#endif
+#ifndef DFDM_XUP_UNROLL
+#define DFDM_XUP_UNROLL 1
+#endif
+#ifndef DFDM_XUP_MINBLOCKS
+#define DFDM_XUP_MINBLOCKS 3
+#endif
 constexpr int kSpmvBatch = DFDM_SPMV_BATCH;
+constexpr int kDirUnroll = DFDM_DIR_UNROLL;
+constexpr int kXupUnroll = DFDM_XUP_UNROLL;
 constexpr int kVecUnroll = DFDM_VEC_UNROLL;
 
 // Ap = K p ; sigma = p . Ap ; alpha = rho / sigma
@@ -421,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv(Plan
             double al = 0.0;
             if (!S.frozen[cc * B + b2] && sigma != 0.0) al = S.rho[cc * B + b2] / sigma;
             if (!isfinite(al)) al = 0.0;
-            S.alpha[cc * B + b2] = al;
+            S.alpha[(size_t)S.aslot * 3 * B + cc * B + b2] = al;
         }
     }
 }
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, DFDM_SPMV_MINBLOCKS) k_pcg_spmv_mf(P
             double al = 0.0;
             if (!S.frozen[cc * B + b2] && sigma != 0.0) al = S.rho[cc * B + b2] / sigma;
             if (!isfinite(al)) al = 0.0;
-            S.alpha[cc * B + b2] = al;
+            S.alpha[(size_t)S.aslot * 3 * B + cc * B + b2] = al;
         }
     }
 }
@@ -511,7 +532,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
     VEC_SETUP();
     double v[2] = {0, 0};
     if (live) {
-        const double al = __ldcg(&S.alpha[c * B + b]);
+        const double al = __ldcg(&S.alpha[(size_t)S.aslot * 3 * B + c * B + b]);
 #pragma unroll(kVecUnroll)
         for (int f = row0; f < nf; f += rstride) {
             size_t o = ((size_t)f * 3 + c) * B + b;
@@ -550,10 +571,11 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_UPD_MINBLOCKS) k_pcg_update(
     }
 }
 
-// x += alpha p ; p = z + beta p   (z = r / diag for Jacobi, the V-cycle output for multigrid)
+// p' = z + beta p   (z = r / diag for Jacobi, the V-cycle output for multigrid); p' goes to the next slot of the ring
 __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_direction(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
                                                               const double* __restrict__ r, const float* __restrict__ z,
-                                                              pvec* __restrict__ p, double* __restrict__ x, PcgScalars S, int xupd, int tag) {
+                                                              const pvec* p, pvec* p_next, PcgScalars S, int tag) {
+    // (p and p_next are the same buffer in the launch before the first iteration: no __restrict__)
     pdl_wait();
     const bool herald = blockIdx.x == 0 && threadIdx.x == 0;
     if (__ldcg(&S.n_active[1 + S.par]) == 0) {             // enqueued past convergence: nothing to do but to say so
@@ -566,6 +588,7 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_directi
     if (herald) {
         const int live_now = __ldcg(&S.n_active[0]);
         S.n_active[1 + (S.par ^ 1)] = live_now;
+        if (tag > 0) S.exec_tag[S.aslot] = tag;            // this iteration ran: its alpha and p count in the x update
         if (tag > 0 && S.host_ring) {
             *reinterpret_cast<volatile unsigned long long*>(S.host_ring + (tag & 3)) = ((unsigned long long)tag << 32) | (unsigned)live_now;
             __threadfence_system();
@@ -574,14 +597,118 @@ __global__ void __launch_bounds__(kVecThreads, DFDM_DIR_MINBLOCKS) k_pcg_directi
     VEC_SETUP();
     if (!live) return;
     const double be = __ldcg(&S.beta[c * B + b]);
-    const double al = xupd ? __ldcg(&S.alpha[c * B + b]) : 0.0;
-#pragma unroll(kVecUnroll)
+#pragma unroll(kDirUnroll)
     for (int f = row0; f < nf; f += rstride) {
         size_t o = ((size_t)f * 3 + c) * B + b;
         double pc = (double)p[o];
-        if (xupd) x[o] += al * pc;
         double zc = z ? (double)z[o] : r[o] * dinv[(size_t)f * B + b];
-        p[o] = (pvec)(zc + be * pc);
+        p_next[o] = (pvec)(zc + be * pc);
+    }
+}
+
+// The same for the multigrid path when B is a multiple of 4: nothing here depends on rows or coordinates any more (no dot
+// product, no x), so the vectors are walked as flat arrays of float4 = four neighbouring designs; beta comes through L1.
+// Sixteen bytes per lane instead of four: the plain kernel, latency bound at full occupancy, reaches 4.2 TB/s on these
+// 4-byte words.
+__global__ void __launch_bounds__(256, 8) k_pcg_direction_v4(long long n4, int groups, const float4* __restrict__ z, const float4* p, float4* p_next,
+                                                            PcgScalars S, int tag) {
+    pdl_wait();
+    const bool herald = blockIdx.x == 0 && threadIdx.x == 0;
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) {
+        if (herald && tag > 0 && S.host_ring) {
+            *reinterpret_cast<volatile unsigned long long*>(S.host_ring + (tag & 3)) = (unsigned long long)tag << 32;
+            __threadfence_system();
+        }
+        return;
+    }
+    if (herald) {
+        const int live_now = __ldcg(&S.n_active[0]);
+        S.n_active[1 + (S.par ^ 1)] = live_now;
+        if (tag > 0) S.exec_tag[S.aslot] = tag;
+        if (tag > 0 && S.host_ring) {
+            *reinterpret_cast<volatile unsigned long long*>(S.host_ring + (tag & 3)) = ((unsigned long long)tag << 32) | (unsigned)live_now;
+            __threadfence_system();
+        }
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double4* beta4 = reinterpret_cast<const double4*>(S.beta);       // [3 B / 4]
+#pragma unroll 2
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 pv = p[i], zv = z[i];
+        const double4 be = beta4[(int)(i % groups)];
+        float4 o;
+        o.x = (float)((double)zv.x + be.x * (double)pv.x);
+        o.y = (float)((double)zv.y + be.y * (double)pv.y);
+        o.z = (float)((double)zv.z + be.z * (double)pv.z);
+        o.w = (float)((double)zv.w + be.w * (double)pv.w);
+        p_next[i] = o;
+    }
+}
+
+// x += sum over the iterations w0 .. w0 + m - 1 (0-based) that executed of alpha_k p_k, both read from their ring slots
+__global__ void __launch_bounds__(kVecThreads, DFDM_XUP_MINBLOCKS) k_pcg_xupdate(int nf, LaneCfg cfg, int B, const pvec* __restrict__ ring,
+                                                              size_t slot_stride, double* __restrict__ x, PcgScalars S, int w0, int m) {
+    pdl_wait();
+    VEC_SETUP();
+    if (!live) return;
+    // the iterations of the window that ran (the same for every thread); the others left stale slots behind, which are not
+    // even read (a stale word may be anything, and 0 x NaN is NaN)
+    const pvec* pj[kXWindow];
+    double al[kXWindow];
+    unsigned ran = 0;
+#pragma unroll
+    for (int j = 0; j < kXWindow; ++j) {
+        const int sl = (w0 + j) % kPRing;
+        const bool ok = j < m && __ldcg(&S.exec_tag[sl]) == w0 + j + 1;
+        pj[j] = ring + (size_t)sl * slot_stride;
+        al[j] = ok ? __ldcg(&S.alpha[(size_t)sl * 3 * B + c * B + b]) : 0.0;
+        ran |= ok ? (1u << j) : 0u;
+    }
+    if (ran == 0) return;
+#pragma unroll(kXupUnroll)
+    for (int f = row0; f < nf; f += rstride) {
+        const size_t o = ((size_t)f * 3 + c) * B + b;
+        pvec v[kXWindow];
+#pragma unroll
+        for (int j = 0; j < kXWindow; ++j) v[j] = (ran >> j) & 1u ? pj[j][o] : (pvec)0;
+        double acc = x[o];
+#pragma unroll
+        for (int j = 0; j < kXWindow; ++j) acc += al[j] * (double)v[j];
+        x[o] = acc;
+    }
+}
+
+// The flat form of the x update for even B: a thread owns two neighbouring designs of one coordinate (the grid is sized so
+// that its stride is a whole number of rows: the step lengths stay in registers) and moves 16 bytes of x per access.
+__global__ void __launch_bounds__(256, 3) k_pcg_xupdate_v2(long long n2, int groups, int B, const float2* __restrict__ ring, size_t slot_stride2,
+                                                          double2* __restrict__ x, PcgScalars S, int w0, int m) {
+    pdl_wait();
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;            // a multiple of groups = 3 B / 2
+    const int g = (int)(t0 % groups);                                      // (coordinate, design pair) of this thread, for every row it visits
+    const float2* pj[kXWindow];
+    double2 al[kXWindow];
+    unsigned ran = 0;
+#pragma unroll
+    for (int j = 0; j < kXWindow; ++j) {
+        const int sl = (w0 + j) % kPRing;
+        const bool ok = j < m && __ldcg(&S.exec_tag[sl]) == w0 + j + 1;
+        pj[j] = ring + (size_t)sl * slot_stride2;
+        al[j] = ok ? __ldcg(reinterpret_cast<const double2*>(S.alpha + (size_t)sl * 3 * B) + g) : make_double2(0.0, 0.0);
+        ran |= ok ? (1u << j) : 0u;
+    }
+    if (ran == 0) return;
+    for (long long i = t0; i < n2; i += stride) {
+        float2 v[kXWindow];
+#pragma unroll
+        for (int j = 0; j < kXWindow; ++j) v[j] = (ran >> j) & 1u ? pj[j][i] : make_float2(0.f, 0.f);
+        double2 acc = x[i];
+#pragma unroll
+        for (int j = 0; j < kXWindow; ++j) {
+            acc.x += al[j].x * (double)v[j].x;
+            acc.y += al[j].y * (double)v[j].y;
+        }
+        x[i] = acc;
     }
 }
 
@@ -2038,7 +2165,7 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
     w.dinv = bump.take<double>(nf * B);
     w.xs = bump.take<double>(nf * 3 * B);
     w.r = bump.take<double>(nf * 3 * B);
-    w.p = bump.take<pvec>(nf * 3 * B);
+    w.p = bump.take<pvec>(nf * 3 * B * kPRing);            // ring of search directions (kernels: k_pcg_direction, k_pcg_xupdate)
     w.r32 = bump.take<float>(nf * 3 * B);
     w.Ap = bump.take<double>(nf * 3 * B);
     w.keep = bump.take<int32_t>(3 * B);
@@ -2062,12 +2189,13 @@ static void carve(Bump& bump, int64_t n, int64_t E, int64_t nf, int64_t nnz, int
     w.lpbar = bump.take<double>(B);
     w.net_loss = bump.take<double>(B);
     w.S.rho = bump.take<double>(3 * B);
-    w.S.alpha = bump.take<double>(3 * B);
+    w.S.alpha = bump.take<double>(3 * B * kPRing);
     w.S.beta = bump.take<double>(3 * B);
     w.S.bb = bump.take<double>(3 * B);
     w.S.partial = bump.take<double>((int64_t)nslabs_max * 6 * B);
     w.S.frozen = bump.take<int32_t>(3 * B);
     w.S.n_active = bump.take<int32_t>(64);
+    w.S.exec_tag = bump.take<int32_t>(64);
     w.S.tickets = bump.take<int32_t>(nchunks_max + 64);
 }
 
@@ -2618,6 +2746,9 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active, 0, sizeof(int32_t), st));
     DFDM_CUDA_OK(cudaMemsetAsync(w.S.n_active + 1, 1, 2 * sizeof(int32_t), st));  // both snapshots: non-zero
     w.S.par = 0;
+    w.S.aslot = 0;
+    DFDM_CUDA_OK(cudaMemsetAsync(w.S.exec_tag, 0, sizeof(int32_t) * kPRing, st));
+    const size_t p_stride = (size_t)P.nf * 3 * B;             // one slot of the ring of search directions
     for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(w.S.host_ring)[k] = 0;   // no kernel of a previous solve is in flight
     k_pcg_init<<<grid, kVecThreads, 0, st>>>(P.nf, cfg, B, w.dinv, w.r, w.xs, w.p, mg ? w.r32 : nullptr, w.S, mg ? 1 : 0, keep);
     DFDM_LAUNCH_OK("k_pcg_init");
@@ -2625,17 +2756,61 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     if (mg) {
         int rc = mg_vcycle(P, *M, base, B, w, 1, st, used, mp, over_w, w_levels);   // z = M r, rho = r.z, beta = 0
         if (rc) return rc;
-        DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0], w.p, w.xs,
-                                                                                   w.S, 0, 0));
+        DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r, w.mg.z[0],
+                                                                                   (const pvec*)w.p, w.p, w.S, 0));
         DFDM_LAUNCH_OK("k_pcg_direction");
         w.S.par ^= 1;
     }
     int it = 0;
+    // multigrid and a batch of whole float4 groups: the flat direction kernel
+    static const bool v4_off = std::getenv("DFDM_DIR_V4") && std::atoi(std::getenv("DFDM_DIR_V4")) == 0;
+    const bool dir_v4 = mg && B % 4 == 0 && !v4_off;
+    const long long dir_n4 = (long long)P.nf * 3 * B / 4;
+    int dir_v4_grid = 0;
+    if (dir_v4) {
+        int dev = 0, sms = 0, per_sm = 0;
+        DFDM_CUDA_OK(cudaGetDevice(&dev));
+        DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_direction_v4, 256, 0));
+        dir_v4_grid = (int)std::min<long long>((dir_n4 + 255) / 256, (long long)sms * std::max(per_sm, 1));
+    }
+    int x_from = 0;                                            // first iteration whose alpha p has not been added to x yet
+    const LaneCfg cfg_xup = one_wave(k_pcg_xupdate, base, P.nf, kVecThreads);
+    // the flat x update: even batch, and a grid whose stride is a whole number of rows
+    int xup_v2_grid = 0;
+    const int xup_groups = 3 * B / 2;
+    if (B % 2 == 0 && !v4_off) {
+        int dev = 0, sms = 0, per_sm = 0;
+        DFDM_CUDA_OK(cudaGetDevice(&dev));
+        DFDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DFDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_xupdate_v2, 256, 0));
+        int a = xup_groups, b2 = 256;
+        while (b2) { int t = a % b2; a = b2; b2 = t; }                     // a = gcd(groups, 256)
+        const int unit = xup_groups / a;                                   // CTAs per whole number of rows
+        xup_v2_grid = (sms * std::max(per_sm, 1)) / unit * unit;
+    }
+    auto flush_x = [&](int upto) -> int {
+        if (upto > x_from && xup_v2_grid > 0) {
+            DFDM_CUDA_OK(launch_chain(k_pcg_xupdate_v2, xup_v2_grid, 256, 0, st, (long long)P.nf * 3 * B / 2, xup_groups, B,
+                                                                                     reinterpret_cast<const float2*>(w.p), p_stride / 2, reinterpret_cast<double2*>(w.xs), w.S,
+                                                                                     x_from, upto - x_from));
+            DFDM_LAUNCH_OK("k_pcg_xupdate");
+        } else if (upto > x_from) {
+            DFDM_CUDA_OK(launch_chain(k_pcg_xupdate, cfg_xup.nchunks * cfg_xup.nslabs, kVecThreads, 0, st, P.nf, cfg_xup, B, (const pvec*)w.p, p_stride, w.xs,
+                                                                                     w.S, x_from, upto - x_from));
+            DFDM_LAUNCH_OK("k_pcg_xupdate");
+        }
+        x_from = upto;
+        return DFDM_OK;
+    };
     auto iteration = [&]() -> int {
+        w.S.aslot = it % kPRing;
+        const pvec* p_cur = w.p + (size_t)(it % kPRing) * p_stride;
+        pvec* p_new = w.p + (size_t)((it + 1) % kPRing) * p_stride;
         if (matrix_free)
-            DFDM_CUDA_OK(launch_chain(k_pcg_spmv_mf, cfg_mf.nchunks * cfg_mf.nslabs, kThreads, 0, st, P, cfg_mf, B, w.qT, w.p, w.Ap, w.S));
+            DFDM_CUDA_OK(launch_chain(k_pcg_spmv_mf, cfg_mf.nchunks * cfg_mf.nslabs, kThreads, 0, st, P, cfg_mf, B, w.qT, p_cur, w.Ap, w.S));
         else
-            DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, w.p, w.Ap, w.S));
+            DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, p_cur, w.Ap, w.S));
         DFDM_LAUNCH_OK("k_pcg_spmv");
         prof_mark(st, 0, used);
         DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r,
@@ -2647,9 +2822,17 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             if (rc) return rc;
             prof_mark(st, -1, used);
         }
-        DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r,
-                                                                                   mg ? w.mg.z[0] : nullptr, w.p, w.xs, w.S, 1, it + 1));
+        if (dir_v4)
+            DFDM_CUDA_OK(launch_chain(k_pcg_direction_v4, dir_v4_grid, 256, 0, st, dir_n4, 3 * B / 4, reinterpret_cast<const float4*>(w.mg.z[0]),
+                                                                                       reinterpret_cast<const float4*>(p_cur), reinterpret_cast<float4*>(p_new), w.S, it + 1));
+        else
+            DFDM_CUDA_OK(launch_chain(k_pcg_direction, cfg_dir.nchunks * cfg_dir.nslabs, kVecThreads, 0, st, P.nf, cfg_dir, B, w.dinv, w.r,
+                                                                                       mg ? w.mg.z[0] : nullptr, p_cur, p_new, w.S, it + 1));
         DFDM_LAUNCH_OK("k_pcg_direction");
+        if (it + 1 - x_from >= kXWindow) {                     // the ring is full: add the window to x before its first slot is reused
+            int rcx = flush_x(it + 1);
+            if (rcx) return rcx;
+        }
         prof_mark(st, 2, used);
         w.S.par ^= 1;
         return DFDM_OK;
@@ -2669,6 +2852,8 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             prof_resolve(used);
             if (*host_flag == 0) break;
         }
+        int rcx = flush_x(it);                                 // what is left of the last window
+        if (rcx) return rcx;
         *iters_out = it;
         return DFDM_OK;
     }
@@ -2720,6 +2905,10 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     for (; checked < it && converged_at < 0; ++checked) {
         int rc = check(checked);
         if (rc) return rc;
+    }
+    {
+        int rcx = flush_x(it);                                 // what is left of the last window (iterations that never ran are skipped)
+        if (rcx) return rcx;
     }
     DFDM_CUDA_OK(cudaStreamSynchronize(st));
     // the iterations enqueued past convergence are empty launches: they must not dilute the per-kernel averages

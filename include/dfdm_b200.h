@@ -270,7 +270,8 @@ DFDM_API const char* dfdm_last_direct_kernel(void);
  */
 #define DFDM_PROF_SPMV 0       /* k_pcg_spmv:      Ap = K p, p.Ap            algorithmic bytes 8 nnz + 36 n_free per design (p is stored in single precision) */
 #define DFDM_PROF_UPDATE 1     /* k_pcg_update:    r -= alpha Ap, r.r (r.z)  84 n_free (multigrid: with the single-precision copy of r the cycle reads) / 80 n_free (Jacobi) */
-#define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: x += alpha p, p = z + beta p   84 n_free (multigrid) / 104 n_free (Jacobi) */
+#define DFDM_PROF_DIRECTION 2  /* k_pcg_direction: p = z + beta p, with its share of k_pcg_xupdate (x += the alpha p of 8 iterations in one
+                                  pass): 54 n_free (multigrid) / 74 n_free (Jacobi) */
 #define DFDM_PROF_MG_DOWN 3    /* k_mg_down, finest level: t = K D^-1 r, restricted residual   4 nnz + 24 n_free + 12 n_coarse (single-precision cycle) */
 #define DFDM_PROF_MG_UP 4      /* k_mg_up, finest level: z = M r, r.z                          4 nnz + 40 n_free + 12 n_coarse */
 #define DFDM_PROF_MG_COARSE 5  /* all kernels below the finest level, per V-cycle */
