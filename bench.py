@@ -407,11 +407,18 @@ def gpu_arm(args, rank, world, local_rank):
         # cycle reads, or 1/diag for Jacobi); direction: p in, p out (12 nf each), z (float) or r + 1/diag, plus its share of
         # k_pcg_xupdate, which adds a window of 8 iterations to x in one pass: (48 + 8 x 12) nf / 8 = 18 nf per iteration
         alg = {"k_pcg_spmv": ((8.0 * E if args.spmv_matrix_free else 8.0 * nnz) + 36.0 * nf) * batch, "k_pcg_update": (84.0 if is_mg else 80.0) * nf * batch,
-               "k_pcg_direction": (54.0 if is_mg else 74.0) * nf * batch,
+               "k_pcg_direction": 0.0,      # set below: depends on how many x windows fall inside the iterations
                # single-precision V-cycle: K D^-1 (4 nnz), r (12 nf), t out (12 nf), coarse rhs out (12 nc)
                "k_mg_down[level 0]": (4.0 * nnz + 24.0 * nf + 12.0 * nc) * batch,
                # K (4 nnz), r (12 nf), t (12 nf), 1/diag (4 nf), coarse solution (12 nc), z out (12 nf)
                "k_mg_up[level 0]": (4.0 * nnz + 40.0 * nf + 12.0 * nc) * batch, "multigrid coarse levels (per V-cycle)": 0.0}
+        # direction: p in, z (or r + 1/diag) in, p out; the x update runs after every 8th iteration of a solve (48 + 8 x 12 n_f bytes) and
+        # is timed with the direction pass before it; what is left of a window at the end of a solve is a pass of its own
+        XW = 8
+        n_it = max(1, iters[0] + iters[1])
+        full_windows = iters[0] // XW + iters[1] // XW
+        alg["k_pcg_direction"] = ((36.0 if is_mg else 56.0) + (48.0 + 12.0 * XW) * full_windows / n_it) * nf * batch
+        x_tail_bytes = sum((48.0 + 12.0 * (k % XW)) * nf * batch for k in iters if k % XW)
         if is_mg:
             alg["multigrid coarse levels (per V-cycle)"] = coarse_cycle_bytes(plan, args.mg_w_levels) * batch
         alg["k_assemble"] = (8.0 * E + 8.0 * nnz + 32.0 * nf) * batch      # q in; K values, 1/diag, b (3 columns) out
@@ -433,12 +440,12 @@ def gpu_arm(args, rank, world, local_rank):
         # cycle and one direction pass without the x update (36 n_f) before the first iteration, then the iterations.
         n_iter = iters[0] + iters[1]
         cyc = alg["k_mg_down[level 0]"] + alg["k_mg_up[level 0]"] + alg["multigrid coarse levels (per V-cycle)"] if is_mg else 0.0
-        # (the x passes at the end of each solve cover a partial window: a few n_f bytes more than the amortised share, not counted)
         step_parts = {"pcg iterations (%d forward + %d adjoint)" % iters: n_iter * it_bytes,
                       "solver start (init, first cycle, first direction) x 2": 2 * (80.0 * nf * batch + cyc + 36.0 * nf * batch),
                       "k_assemble": alg["k_assemble"], "state, loss and reverse edge kernels": alg["state, loss and reverse edge kernels (5 launches)"],
                       "hierarchy set-up (single-precision copies, Galerkin sums)": mg_setup_bytes(plan) * batch if is_mg else 0.0,
-                      "k_edge_dq": (40.0 * E + 24.0 * plan.n) * batch, "layout changes of q and dq": 32.0 * E * batch}
+                      "k_edge_dq": (40.0 * E + 24.0 * plan.n) * batch, "layout changes of q and dq": 32.0 * E * batch,
+                      "x updates of the last, partial windows": x_tail_bytes}
         step_bytes = sum(step_parts.values())
         ms_step = ms_total / args.steps
         top = max((kk for kk in kernels if kk["algorithmic_bytes"] > 0), key=lambda kk: kk["share_of_step"])
