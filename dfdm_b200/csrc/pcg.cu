@@ -1009,6 +1009,107 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
     }
 }
 
+// k_pcg_spmv with TWO designs per thread (even B): 16-byte matrix values, 8-byte gathers of p, half the index loads per
+// design.  The product is latency bound at 64 registers and four CTAs per SM; this form keeps three CTAs per SM, each
+// thread with twice the bytes in flight.  Same arithmetic and summation order per design.
+__global__ void __launch_bounds__(kThreads, 3) k_pcg_spmv_v2(PlanDev P, LaneCfg cfg, int B, const double* __restrict__ vals,
+                                                            const pvec* __restrict__ p, double* __restrict__ Ap, PcgScalars S) {
+    constexpr int V = 2;
+    pdl_wait();
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
+    LANE_SETUP_V();
+    double dsum[3][V];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) dsum[c][v] = 0.0;
+    if (live) {
+        const int W = P.ell_w;
+        const size_t sB = (size_t)B;
+        const pvec* pb = p + b;
+        const double* vb = vals + b;
+        TILE_ROWS(f, P.nf) {
+            const int k0 = P.rowptr[f], k1 = P.rowptr[f + 1];
+            int col[kSpmvBatch];
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) col[u] = u < W ? P.ell_col[(size_t)f * W + u] : f;
+            double2 a[kSpmvBatch];
+            float2 x0[kSpmvBatch], x1[kSpmvBatch], x2[kSpmvBatch];
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) {
+                a[u] = k0 + u < k1 ? *reinterpret_cast<const double2*>(vb + (size_t)(k0 + u) * sB) : make_double2(0.0, 0.0);
+                const pvec* pj = pb + (size_t)col[u] * 3 * sB;
+                x0[u] = *reinterpret_cast<const float2*>(pj);
+                x1[u] = *reinterpret_cast<const float2*>(pj + sB);
+                x2[u] = *reinterpret_cast<const float2*>(pj + 2 * sB);
+            }
+            const size_t od = (size_t)f * 3 * sB + b;
+            const float2 d0 = *reinterpret_cast<const float2*>(p + od), d1 = *reinterpret_cast<const float2*>(p + od + sB),
+                         d2 = *reinterpret_cast<const float2*>(p + od + 2 * sB);
+            double2 r0 = make_double2(0.0, 0.0), r1 = r0, r2 = r0;
+#pragma unroll
+            for (int u = 0; u < kSpmvBatch; ++u) {
+                r0.x += a[u].x * (double)x0[u].x; r0.y += a[u].y * (double)x0[u].y;
+                r1.x += a[u].x * (double)x1[u].x; r1.y += a[u].y * (double)x1[u].y;
+                r2.x += a[u].x * (double)x2[u].x; r2.y += a[u].y * (double)x2[u].y;
+            }
+            for (int k = k0 + kSpmvBatch; k < k1; ++k) {          // rows wider than one batch
+                const double2 ak = *reinterpret_cast<const double2*>(vb + (size_t)k * sB);
+                const pvec* pj = pb + (size_t)P.colidx[k] * 3 * sB;
+                const float2 y0 = *reinterpret_cast<const float2*>(pj), y1 = *reinterpret_cast<const float2*>(pj + sB),
+                             y2 = *reinterpret_cast<const float2*>(pj + 2 * sB);
+                r0.x += ak.x * (double)y0.x; r0.y += ak.y * (double)y0.y;
+                r1.x += ak.x * (double)y1.x; r1.y += ak.y * (double)y1.y;
+                r2.x += ak.x * (double)y2.x; r2.y += ak.y * (double)y2.y;
+            }
+            *reinterpret_cast<double2*>(Ap + od) = r0;
+            *reinterpret_cast<double2*>(Ap + od + sB) = r1;
+            *reinterpret_cast<double2*>(Ap + od + 2 * sB) = r2;
+            dsum[0][0] += (double)d0.x * r0.x; dsum[0][1] += (double)d0.y * r0.y;
+            dsum[1][0] += (double)d1.x * r1.x; dsum[1][1] += (double)d1.y * r1.y;
+            dsum[2][0] += (double)d2.x * r2.x; dsum[2][1] += (double)d2.y * r2.y;
+        }
+    }
+    // per-design partials: registers -> shared memory -> one partial per (slab, design); last CTA of the chunk finishes
+    __shared__ double red[3 * V][kThreads];
+    __shared__ int s_last;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) red[c * V + v][threadIdx.x] = dsum[c][v];
+    __syncthreads();
+    if (rl == 0 && live) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double s = 0.0;
+                for (int r = 0; r < cfg.rstep; ++r) s += red[c * V + v][(r << cfg.shift) + bl];
+                S.partial[((size_t)slab * 3 + c) * B + b + v] = s;
+            }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tk = atomicAdd(&S.tickets[chunk], 1);
+        s_last = (tk == cfg.nslabs - 1);
+        if (s_last) S.tickets[chunk] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int idx = threadIdx.x; idx < 3 * cbl * V; idx += blockDim.x) {
+            int cc = idx / (cbl * V), b2 = chunk * cbl * V + idx % (cbl * V);
+            if (b2 >= B) continue;
+            double sigma = sum_slabs<3>(S.partial, cc, b2, B, cfg.nslabs);
+            double al = 0.0;
+            if (!S.frozen[cc * B + b2] && sigma != 0.0) al = S.rho[cc * B + b2] / sigma;
+            if (!isfinite(al)) al = 0.0;
+            S.alpha[(size_t)S.aslot * 3 * B + cc * B + b2] = al;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // The small levels of the hierarchy in ONE launch.  Below ~1 500 rows a level moves almost nothing and each of
 // its kernels costs a launch plus a chain of dependent loads (8-15 us); the plain V-cycle through those levels
@@ -2734,6 +2835,9 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     const LaneCfg cfg = one_wave(k_pcg_init, base, P.nf, kVecThreads);
     static const int spmv_tiles = tile_factor("DFDM_TILE_SPMV", 4);
     const LaneCfg cfg_spmv = rows_cfg(k_pcg_spmv, base, P.nf, spmv_tiles);
+    static const bool spmv2_off = std::getenv("DFDM_SPMV_V2") && std::atoi(std::getenv("DFDM_SPMV_V2")) == 0;
+    const bool spmv_v2 = B % 2 == 0 && !spmv2_off;              // two designs per thread
+    const LaneCfg cfg_spmv2 = spmv_v2 ? rows_cfg(k_pcg_spmv_v2, vec_base(B, 2), P.nf, spmv_tiles) : cfg_spmv;
     const bool matrix_free = (opt.flags & DFDM_FLAG_SPMV_MATRIX_FREE) != 0 && P.inc_w > 0;
     const LaneCfg cfg_mf = rows_cfg(k_pcg_spmv_mf, base, P.nf, spmv_tiles);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
@@ -2809,6 +2913,8 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
         pvec* p_new = w.p + (size_t)((it + 1) % kPRing) * p_stride;
         if (matrix_free)
             DFDM_CUDA_OK(launch_chain(k_pcg_spmv_mf, cfg_mf.nchunks * cfg_mf.nslabs, kThreads, 0, st, P, cfg_mf, B, w.qT, p_cur, w.Ap, w.S));
+        else if (spmv_v2)
+            DFDM_CUDA_OK(launch_chain(k_pcg_spmv_v2, cfg_spmv2.nchunks * cfg_spmv2.nslabs, kThreads, 0, st, P, cfg_spmv2, B, w.vals, p_cur, w.Ap, w.S));
         else
             DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, p_cur, w.Ap, w.S));
         DFDM_LAUNCH_OK("k_pcg_spmv");
