@@ -1009,6 +1009,102 @@ __global__ void __launch_bounds__(kThreads, 4) k_mg_up(MgMat A, MgLevelDev L, La
     }
 }
 
+// k_pcg_update with TWO designs per thread (even B): a thread takes a row's three coordinates for a design pair, 16 bytes
+// per access.  Same update per entry; the partial sums of r.r are grouped differently (rounding-level differences in a
+// number that is only compared with the stop test).
+__global__ void __launch_bounds__(kThreads, 3) k_pcg_update_v2(int nf, LaneCfg cfg, int B, const double* __restrict__ dinv,
+                                                              const double* __restrict__ Ap, double* __restrict__ r, float* __restrict__ r32,
+                                                              PcgScalars S, double tol2, int mg) {
+    constexpr int V = 2;
+    pdl_wait();
+    if (__ldcg(&S.n_active[1 + S.par]) == 0) return;
+    LANE_SETUP_V();
+    double ds[6][V];                     // [0..2]: r . r / diag per coordinate (Jacobi), [3..5]: r . r
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int v = 0; v < V; ++v) ds[k][v] = 0.0;
+    if (live) {
+        const size_t sB = (size_t)B;
+        double2 al[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) al[c] = __ldcg(reinterpret_cast<const double2*>(S.alpha + (size_t)S.aslot * 3 * B + c * B + b));
+        TILE_ROWS(f, nf) {
+            const size_t o = (size_t)f * 3 * sB + b;
+            double2 rc[3], ap[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                rc[c] = *reinterpret_cast<const double2*>(r + o + c * sB);
+                ap[c] = *reinterpret_cast<const double2*>(Ap + o + c * sB);
+            }
+            const double2 di = mg ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(dinv + (size_t)f * sB + b);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                rc[c].x -= al[c].x * ap[c].x;
+                rc[c].y -= al[c].y * ap[c].y;
+                *reinterpret_cast<double2*>(r + o + c * sB) = rc[c];
+                if (r32) *reinterpret_cast<float2*>(r32 + o + c * sB) = make_float2((float)rc[c].x, (float)rc[c].y);
+                ds[c][0] += rc[c].x * rc[c].x * di.x;
+                ds[c][1] += rc[c].y * rc[c].y * di.y;
+                ds[3 + c][0] += rc[c].x * rc[c].x;
+                ds[3 + c][1] += rc[c].y * rc[c].y;
+            }
+        }
+    }
+    __shared__ double red[6 * V][kThreads];
+    __shared__ int s_last;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int v = 0; v < V; ++v) red[k * V + v][threadIdx.x] = ds[k][v];
+    __syncthreads();
+    if (rl == 0 && live) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double s2 = 0.0;
+                for (int q = 0; q < cfg.rstep; ++q) s2 += red[k * V + v][(q << cfg.shift) + bl];
+                S.partial[((size_t)slab * 6 + k) * B + b + v] = s2;
+            }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tk = atomicAdd(&S.tickets[chunk], 1);
+        s_last = (tk == cfg.nslabs - 1);
+        if (s_last) S.tickets[chunk] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        int done = 0;
+        for (int idx = threadIdx.x; idx < 3 * cbl * V; idx += blockDim.x) {
+            int cc = idx / (cbl * V), b2 = chunk * cbl * V + idx % (cbl * V);
+            if (b2 >= B) continue;
+            int o = cc * B + b2;
+            if (S.frozen[o]) { S.beta[o] = 0.0; continue; }
+            double rho_new = sum_slabs<6>(S.partial, cc, b2, B, cfg.nslabs);
+            double rr = sum_slabs<6>(S.partial, 3 + cc, b2, B, cfg.nslabs);
+            if (!mg) {
+                double rho_old = S.rho[o];
+                double be = rho_old != 0.0 ? rho_new / rho_old : 0.0;
+                if (!isfinite(be)) be = 0.0;
+                S.beta[o] = be;
+                S.rho[o] = rho_new;
+            }
+            if (!isfinite(rr)) {
+                S.frozen[o] = 2;
+                done += 1;
+            } else if (rr <= tol2 * S.bb[o]) {
+                S.frozen[o] = 1;
+                done += 1;
+            }
+        }
+        if (done) atomicSub(S.n_active, done);
+    }
+}
+
 // k_pcg_spmv with TWO designs per thread (even B): 16-byte matrix values, 8-byte gathers of p, half the index loads per
 // design.  The product is latency bound at 64 registers and four CTAs per SM; this form keeps three CTAs per SM, each
 // thread with twice the bytes in flight.  Same arithmetic and summation order per design.
@@ -2838,6 +2934,9 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
     static const bool spmv2_off = std::getenv("DFDM_SPMV_V2") && std::atoi(std::getenv("DFDM_SPMV_V2")) == 0;
     const bool spmv_v2 = B % 2 == 0 && !spmv2_off;              // two designs per thread
     const LaneCfg cfg_spmv2 = spmv_v2 ? rows_cfg(k_pcg_spmv_v2, vec_base(B, 2), P.nf, spmv_tiles) : cfg_spmv;
+    static const bool upd2_off = std::getenv("DFDM_UPDATE_V2") && std::atoi(std::getenv("DFDM_UPDATE_V2")) == 0;
+    const bool upd_v2 = B % 2 == 0 && !upd2_off;
+    const LaneCfg cfg_upd2 = upd_v2 ? rows_cfg(k_pcg_update_v2, vec_base(B, 2), P.nf) : LaneCfg{};
     const bool matrix_free = (opt.flags & DFDM_FLAG_SPMV_MATRIX_FREE) != 0 && P.inc_w > 0;
     const LaneCfg cfg_mf = rows_cfg(k_pcg_spmv_mf, base, P.nf, spmv_tiles);
     const LaneCfg cfg_upd = one_wave(k_pcg_update, base, P.nf, kVecThreads);
@@ -2919,8 +3018,12 @@ static int pcg_solve_once(const PlanDev& P, const MgDev* M, const LaneCfg& base,
             DFDM_CUDA_OK(launch_chain(k_pcg_spmv, cfg_spmv.nchunks * cfg_spmv.nslabs, kThreads, 0, st, P, cfg_spmv, B, w.vals, p_cur, w.Ap, w.S));
         DFDM_LAUNCH_OK("k_pcg_spmv");
         prof_mark(st, 0, used);
-        DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r,
-                                                                                mg ? w.r32 : (float*)nullptr, w.S, rtol * rtol, mg ? 1 : 0));
+        if (upd_v2)
+            DFDM_CUDA_OK(launch_chain(k_pcg_update_v2, cfg_upd2.nchunks * cfg_upd2.nslabs, kThreads, 0, st, P.nf, cfg_upd2, B, w.dinv, w.Ap, w.r,
+                                                                                    mg ? w.r32 : (float*)nullptr, w.S, rtol * rtol, mg ? 1 : 0));
+        else
+            DFDM_CUDA_OK(launch_chain(k_pcg_update, cfg_upd.nchunks * cfg_upd.nslabs, kVecThreads, 0, st, P.nf, cfg_upd, B, w.dinv, w.Ap, w.r,
+                                                                                    mg ? w.r32 : (float*)nullptr, w.S, rtol * rtol, mg ? 1 : 0));
         DFDM_LAUNCH_OK("k_pcg_update");
         prof_mark(st, 1, used);
         if (mg) {
