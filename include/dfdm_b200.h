@@ -58,6 +58,11 @@ extern "C" {
                                   factor fits; asked for by name beyond that, the same factorisation with the band in global memory
                                   (slow; the path that solves the indefinite K of a mixed-sign q at any size) */
 #define DFDM_SOLVER_PCG 2      /* CG on batch-interleaved CSR, preconditioned by aggregation multigrid (or Jacobi: DFDM_PRECOND_*) */
+/* Precision of the PCG path: the solution x, the residual r, K, K p and every dot product are double precision, and x and r
+   move by the same stored vector (x += a p, r -= a K p), so r stays the true residual of x to double-precision rounding and
+   the stop tests below bound the true error.  Single precision is used where it cannot reach the answer: the multigrid
+   preconditioner (its operators, vectors and its copy of r) and the STORED search direction p (rounding p tilts the
+   direction by 6e-8, like an inexact preconditioner: same iteration counts, same errors against SuperLU). */
 
 typedef struct dfdm_plan dfdm_plan;
 typedef struct dfdm_goalprog dfdm_goalprog;
