@@ -97,3 +97,48 @@ def test_plan_hierarchy_converges_like_the_gpu_path(mesh, bound):
     # the plain V-cycle needs visibly more iterations on the same hierarchy: the W levels are doing their job
     iters_v, _ = pcg_iterations(A0, b, lambda r: cycle(levels, inv, 0, r, 0, over=1.7, over_w=1.7))
     assert iters_v > iters
+
+
+def pcg_as_the_kernels_store_it(A, b, M, rtol=1e-12, maxit=300, window=8):
+    """The recurrence of csrc/pcg.cu with its storage choices: the search direction rounded to single precision every time it is
+    stored, the multigrid cycle fed a single-precision copy of r, and x updated once per window of iterations from the kept
+    directions and step lengths; K p, the dot products, x and r in double precision."""
+    f32 = lambda v: v.astype(np.float32).astype(np.float64)
+    x = np.zeros_like(b); r = b.copy(); z = M(f32(r)); p = f32(z)
+    rz = np.sum(r * z, axis=0); bb = np.sum(b * b, axis=0)
+    kept = []
+    for it in range(1, maxit + 1):
+        Ap = A @ p
+        alpha = rz / np.sum(p * Ap, axis=0)
+        kept.append((alpha, p))
+        r -= alpha * Ap
+        done = np.all(np.sum(r * r, axis=0) <= rtol ** 2 * bb)
+        if len(kept) == window or done:
+            for a_k, p_k in kept:
+                x += a_k * p_k
+            kept = []
+        if done:
+            return it, x
+        z = M(f32(r)); rz_new = np.sum(r * z, axis=0)
+        p = f32(z + (rz_new / rz) * p); rz = rz_new
+    return maxit, x
+
+
+def test_single_precision_directions_and_windowed_x_updates_change_nothing():
+    """What DESIGN.md section 4.2 claims for the storage choices of the PCG kernels, on the CPU: the same iteration count as
+    the all-double recurrence and the same solution to rounding, because x and r move by the same stored vector."""
+    edges, fixed, _, _, _ = W.grid_arrays(64)
+    plan = Plan(len(fixed), edges, fixed)
+    rng = np.random.default_rng(4)
+    q = 1.0 + 0.3 * (rng.random(len(edges)) - 0.5)
+    K = stiffness(plan, edges, fixed, q)
+    perm, levels, inv = hierarchy(plan, K)
+    A0 = levels[0][0]
+    b = rng.standard_normal((A0.shape[0], 3))
+    w_levels = min(3, len(levels) - 1)
+    M = lambda r: cycle(levels, inv, 0, r.astype(np.float32).astype(np.float64), w_levels).astype(np.float32).astype(np.float64)
+    it_ref, x_ref = pcg_iterations(A0, b, M)
+    it_new, x_new = pcg_as_the_kernels_store_it(A0, b, M)
+    assert it_new == it_ref and it_ref > 8                      # more than one window
+    assert np.max(np.abs(x_new - x_ref)) <= 1e-11 * np.max(np.abs(x_ref))
+    assert np.max(np.abs(A0 @ x_new - b)) <= 1e-10 * np.max(np.abs(b))
