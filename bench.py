@@ -452,6 +452,7 @@ def gpu_arm(args, rank, world, local_rank):
         line["roofline"] = {"bound": "hbm", "kernel": "whole step; dominant group: " + top["kernel"], "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                             "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                             "traffic": traffic_for(top["kernel"], wl["name"]), "peak_source": peak_src,
+                            "traffic_of": "the dominant group, DRAM bytes read + written per launch (group: per cycle) from ncu --set full (profiles/traffic.json); its algorithmic bytes are under 'kernels'",
                             "what": "algorithmic bytes of one whole step (step_bytes) / ms_per_step / peak; per-kernel and per-group numbers under 'kernels'",
                             "step_bytes": step_bytes, "step_bytes_parts": step_parts,
                             "dominant": {"kernel": top["kernel"], "share_of_step": top["share_of_step"], "achieved": top["achieved_gbs"],
